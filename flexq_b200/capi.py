@@ -1,0 +1,203 @@
+"""ctypes binding of libflexq_b200.so (the C ABI declared in include/flexq_b200.h).
+
+PyTorch is plumbing only: tensors give device memory (``data_ptr()``) and the current CUDA
+stream.  There is no CPU fallback -- if the library is missing or a call fails this module
+raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflexq_b200.so")
+
+GROUP = 128
+ROUND_CUDA = 0
+ROUND_PYTHON = 1
+
+_vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/flexq_b200.h one to one
+_SIGNATURES = {
+    "flexq_version": (_i, []),
+    "flexq_status_string": (ctypes.c_char_p, [_i]),
+    "flexq_w6_packed_bytes": (_sz, [_i, _i]),
+    "flexq_planes_bytes": (_sz, [_i, _i, _i]),
+    "flexq_sx_ld": (_i, [_i]),
+    "flexq_xscale_ref_halves": (_sz, [_i, _i]),
+    "flexq_gemm_workspace_bytes": (_sz, []),
+    "flexq_linear_workspace_bytes": (_sz, [_i, _i]),
+    "flexq_workspace_init": (_i, [_vp, _sz, _vp]),
+    "flexq_bit_packing_i32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "flexq_bit_packing_f16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "flexq_quant_act": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "flexq_pack_w6_i32": (_i, [_vp, _vp, _i, _i, _vp]),
+    "flexq_pack_w6_i8": (_i, [_vp, _vp, _i, _i, _vp]),
+    "flexq_quant_pack_w6_f16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "flexq_quant_pack_w6_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "flexq_planes_to_i8": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "flexq_planes_to_w6": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "flexq_xscale_ref_to_sx": (_i, [_vp, _vp, _i, _i, _vp]),
+    "flexq_w6_to_i8": (_i, [_vp, _vp, _i, _i, _vp]),
+    "flexq_gemm_w6ax": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "flexq_gemm_w6ax_groupsums": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "flexq_linear_w6ax_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "flexq_gemm_ref_layout": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class FlexQError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FlexQError(
+                f"{LIB_PATH} not found: build it with `python -m flexq_b200.build` "
+                "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = load().flexq_status_string(status).decode()
+        raise FlexQError(f"{what} failed: status {status} ({msg})")
+
+
+def _ptr(t: torch.Tensor):
+    assert t.is_cuda and t.is_contiguous(), "flexq_b200 needs contiguous CUDA tensors"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ceil4(m: int) -> int:
+    return (m + 3) // 4 * 4
+
+
+# ------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (allocate outputs with torch, call the C ABI on the current stream)
+# ------------------------------------------------------------------------------------------
+def new_workspace(M: int | None = None, K: int | None = None, device="cuda") -> torch.Tensor:
+    lib = load()
+    n = lib.flexq_gemm_workspace_bytes() if M is None else lib.flexq_linear_workspace_bytes(M, K)
+    return torch.zeros(n, dtype=torch.uint8, device=device)
+
+
+def bit_packing_i32(ints: torch.Tensor, bits: int) -> torch.Tensor:
+    R, K = ints.shape
+    out = torch.empty(R * K * bits // 32, dtype=torch.int32, device=ints.device)
+    check(load().flexq_bit_packing_i32(_ptr(ints), _ptr(out), R, K, bits, _stream()), "flexq_bit_packing_i32")
+    return out
+
+
+def bit_packing_f16(x: torch.Tensor, bits: int):
+    M, K = x.shape
+    planes = torch.empty(M * K * bits // 32, dtype=torch.int32, device=x.device)
+    xs = torch.empty(K // GROUP, 2 * ceil4(M), dtype=torch.float16, device=x.device)
+    check(load().flexq_bit_packing_f16(_ptr(x), _ptr(planes), _ptr(xs), M, K, bits, _stream()), "flexq_bit_packing_f16")
+    return planes, xs
+
+
+def quant_act(x: torch.Tensor, bits: int, mode: int = ROUND_CUDA):
+    M, K = x.shape
+    xq = torch.empty(M, K, dtype=torch.int8, device=x.device)
+    sx = torch.empty(K // GROUP, ceil4(M), dtype=torch.float32, device=x.device)
+    check(load().flexq_quant_act(_ptr(x), _ptr(xq), _ptr(sx), M, K, bits, mode, _stream()), "flexq_quant_act")
+    return xq, sx
+
+
+def _new_w6(N, K, device):
+    return torch.empty(load().flexq_w6_packed_bytes(N, K), dtype=torch.uint8, device=device)
+
+
+def pack_w6(w_int: torch.Tensor) -> torch.Tensor:
+    N, K = w_int.shape
+    w6 = _new_w6(N, K, w_int.device)
+    fn = {torch.int32: "flexq_pack_w6_i32", torch.int8: "flexq_pack_w6_i8"}[w_int.dtype]
+    check(getattr(load(), fn)(_ptr(w_int), _ptr(w6), N, K, _stream()), fn)
+    return w6
+
+
+def quant_pack_w6(w: torch.Tensor):
+    N, K = w.shape
+    w6 = _new_w6(N, K, w.device)
+    ws = torch.empty(K // GROUP, N, dtype=torch.float16, device=w.device)
+    fn = {torch.float16: "flexq_quant_pack_w6_f16", torch.float32: "flexq_quant_pack_w6_f32"}[w.dtype]
+    check(getattr(load(), fn)(_ptr(w), _ptr(w6), _ptr(ws), N, K, _stream()), fn)
+    return w6, ws
+
+
+def planes_to_i8(planes: torch.Tensor, R: int, K: int, bits: int) -> torch.Tensor:
+    out = torch.empty(R, K, dtype=torch.int8, device=planes.device)
+    check(load().flexq_planes_to_i8(_ptr(planes), _ptr(out), R, K, bits, _stream()), "flexq_planes_to_i8")
+    return out
+
+
+def planes_to_w6(planes: torch.Tensor, N: int, K: int) -> torch.Tensor:
+    w6 = _new_w6(N, K, planes.device)
+    scratch = torch.empty(N, K, dtype=torch.int8, device=planes.device)
+    check(load().flexq_planes_to_w6(_ptr(planes), _ptr(w6), _ptr(scratch), N, K, _stream()), "flexq_planes_to_w6")
+    return w6
+
+
+def xscale_ref_to_sx(xs: torch.Tensor, M: int, K: int) -> torch.Tensor:
+    sx = torch.empty(K // GROUP, ceil4(M), dtype=torch.float32, device=xs.device)
+    check(load().flexq_xscale_ref_to_sx(_ptr(xs), _ptr(sx), M, K, _stream()), "flexq_xscale_ref_to_sx")
+    return sx
+
+
+def w6_to_i8(w6: torch.Tensor, N: int, K: int) -> torch.Tensor:
+    out = torch.empty(N, K, dtype=torch.int8, device=w6.device)
+    check(load().flexq_w6_to_i8(_ptr(w6), _ptr(out), N, K, _stream()), "flexq_w6_to_i8")
+    return out
+
+
+def gemm_w6ax(xq, sx, w6, w_scale, N: int, workspace: torch.Tensor, out: torch.Tensor | None = None):
+    M, K = xq.shape
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float16, device=xq.device)
+    check(load().flexq_gemm_w6ax(_ptr(xq), _ptr(sx), _ptr(w6), _ptr(w_scale), _ptr(out), M, N, K,
+                                 _ptr(workspace), workspace.numel(), _stream()), "flexq_gemm_w6ax")
+    return out
+
+
+def gemm_w6ax_groupsums(xq, w6, N: int) -> torch.Tensor:
+    M, K = xq.shape
+    S = torch.empty(M, N, K // GROUP, dtype=torch.int32, device=xq.device)
+    check(load().flexq_gemm_w6ax_groupsums(_ptr(xq), _ptr(w6), _ptr(S), M, N, K, _stream()), "flexq_gemm_w6ax_groupsums")
+    return S
+
+
+def linear_w6ax(x, w6, w_scale, N: int, x_bits: int, workspace: torch.Tensor, mode: int = ROUND_CUDA,
+                out: torch.Tensor | None = None):
+    M, K = x.shape
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float16, device=x.device)
+    check(load().flexq_linear_w6ax_f16(_ptr(x), _ptr(w6), _ptr(w_scale), _ptr(out), M, N, K, x_bits, mode,
+                                       _ptr(workspace), workspace.numel(), _stream()), "flexq_linear_w6ax_f16")
+    return out
+
+
+def gemm_ref_layout(x_planes, x_scale, w6, w_scale, M: int, N: int, K: int, x_bits: int, workspace: torch.Tensor):
+    out = torch.empty(M, N, dtype=torch.float16, device=w6.device)
+    check(load().flexq_gemm_ref_layout(_ptr(x_planes), _ptr(x_scale), _ptr(w6), _ptr(w_scale), _ptr(out), M, N, K, x_bits,
+                                       _ptr(workspace), workspace.numel(), _stream()), "flexq_gemm_ref_layout")
+    return out

@@ -1,0 +1,126 @@
+// extern "C" boundary of libflexq_b200.so -- see include/flexq_b200.h for the contract and the
+// reference interfaces each entry point replaces.  No torch types, no allocation, no sync.
+#include "common.cuh"
+
+namespace flexq {
+int quant_act_native(const __half*, int8_t*, float*, int, int, int, int, cudaStream_t);
+int quant_act_planes(const __half*, uint32_t*, __half*, int, int, int, cudaStream_t);
+template <typename T> int pack_w6(const T*, uint8_t*, int, int, cudaStream_t);
+template <typename T> int quant_pack_w6(const T*, uint8_t*, __half*, int, int, cudaStream_t);
+int unpack_w6(const uint8_t*, int8_t*, int, int, cudaStream_t);
+int pack_planes_i32(const int32_t*, uint32_t*, int, int, int, cudaStream_t);
+int planes_to_i8(const uint32_t*, int8_t*, int, int, int, cudaStream_t);
+int xscale_ref_to_sx(const __half*, float*, int, int, cudaStream_t);
+int gemm_w6ax(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, size_t, cudaStream_t);
+int gemm_w6ax_groupsums(const int8_t*, const uint8_t*, int32_t*, int, int, int, cudaStream_t);
+}  // namespace flexq
+
+using namespace flexq;
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+int flexq_version(void) { return 100; }
+
+const char* flexq_status_string(int s) {
+    switch (s) {
+        case FLEXQ_OK: return "ok";
+        case FLEXQ_ERR_BAD_SHAPE: return "bad shape (need K % 128 == 0, K >= 128, positive M/N; plane layouts need R % min(R,8) == 0)";
+        case FLEXQ_ERR_BAD_BITS: return "unsupported bit width";
+        case FLEXQ_ERR_NULL: return "null pointer";
+        case FLEXQ_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case FLEXQ_ERR_NO_DEVICE: return "no usable sm_100 device / driver entry point";
+        case FLEXQ_ERR_TENSORMAP: return "cuTensorMapEncodeTiled failed";
+        default: return s > 0 ? cudaGetErrorString((cudaError_t)s) : "unknown flexq status";
+    }
+}
+
+size_t flexq_w6_packed_bytes(int N, int K) { return (size_t)ceil_div(N, kTileN) * (size_t)(K / kGroup) * kTileBytes; }
+size_t flexq_planes_bytes(int R, int K, int bits) { return (size_t)R * K / 8 * bits; }
+int flexq_sx_ld(int M) { return ceil4(M); }
+size_t flexq_xscale_ref_halves(int M, int K) { return (size_t)(K / kGroup) * 2 * ceil4(M); }
+size_t flexq_gemm_workspace_bytes(void) { return kCntBytes + (size_t)kMaxCtas * kSlotFloats * sizeof(float); }
+size_t flexq_linear_workspace_bytes(int M, int K) {
+    return flexq_gemm_workspace_bytes() + align_up((size_t)M * K, 256) + align_up((size_t)(K / kGroup) * ceil4(M) * sizeof(float), 256);
+}
+
+int flexq_workspace_init(void* ws, size_t bytes, void* stream) {
+    if (!ws) return FLEXQ_ERR_NULL;
+    return (int)cudaMemsetAsync(ws, 0, bytes, (cudaStream_t)stream);
+}
+
+int flexq_bit_packing_i32(const int32_t* in, int32_t* planes, int R, int K, int bits, void* stream) {
+    return pack_planes_i32(in, reinterpret_cast<uint32_t*>(planes), R, K, bits, (cudaStream_t)stream);
+}
+
+int flexq_bit_packing_f16(const void* x, int32_t* planes, void* xs, int M, int K, int bits, void* stream) {
+    return quant_act_planes((const __half*)x, reinterpret_cast<uint32_t*>(planes), (__half*)xs, M, K, bits, (cudaStream_t)stream);
+}
+
+int flexq_quant_act(const void* x, int8_t* xq, float* sx, int M, int K, int bits, int mode, void* stream) {
+    return quant_act_native((const __half*)x, xq, sx, M, K, bits, mode, (cudaStream_t)stream);
+}
+
+int flexq_pack_w6_i32(const int32_t* w, uint8_t* w6, int N, int K, void* stream) { return pack_w6<int32_t>(w, w6, N, K, (cudaStream_t)stream); }
+int flexq_pack_w6_i8(const int8_t* w, uint8_t* w6, int N, int K, void* stream) { return pack_w6<int8_t>(w, w6, N, K, (cudaStream_t)stream); }
+int flexq_quant_pack_w6_f16(const void* w, uint8_t* w6, void* ws, int N, int K, void* stream) {
+    return quant_pack_w6<__half>((const __half*)w, w6, (__half*)ws, N, K, (cudaStream_t)stream);
+}
+int flexq_quant_pack_w6_f32(const float* w, uint8_t* w6, void* ws, int N, int K, void* stream) {
+    return quant_pack_w6<float>(w, w6, (__half*)ws, N, K, (cudaStream_t)stream);
+}
+
+int flexq_planes_to_i8(const int32_t* planes, int8_t* out, int R, int K, int bits, void* stream) {
+    return planes_to_i8(reinterpret_cast<const uint32_t*>(planes), out, R, K, bits, (cudaStream_t)stream);
+}
+int flexq_planes_to_w6(const int32_t* planes, uint8_t* w6, int8_t* scratch, int N, int K, void* stream) {
+    if (!scratch) return FLEXQ_ERR_NULL;
+    int e = planes_to_i8(reinterpret_cast<const uint32_t*>(planes), scratch, N, K, 6, (cudaStream_t)stream);
+    if (e) return e;
+    return pack_w6<int8_t>(scratch, w6, N, K, (cudaStream_t)stream);
+}
+int flexq_xscale_ref_to_sx(const void* xs, float* sx, int M, int K, void* stream) {
+    return xscale_ref_to_sx((const __half*)xs, sx, M, K, (cudaStream_t)stream);
+}
+int flexq_w6_to_i8(const uint8_t* w6, int8_t* out, int N, int K, void* stream) { return unpack_w6(w6, out, N, K, (cudaStream_t)stream); }
+
+int flexq_gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale, void* d, int M, int N, int K,
+                    void* ws, size_t ws_bytes, void* stream) {
+    return gemm_w6ax(xq, sx, w6, (const __half*)w_scale, (__half*)d, M, N, K, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K, void* stream) {
+    return gemm_w6ax_groupsums(xq, w6, S, M, N, K, (cudaStream_t)stream);
+}
+
+// workspace layout for the fused / reference-layout entries: [gemm workspace][Xq][sx]
+static int carve(void* ws, size_t ws_bytes, int M, int K, int8_t** xq, float** sx) {
+    if (!ws) return FLEXQ_ERR_NULL;
+    if (M <= 0 || K < kGroup || K % kGroup) return FLEXQ_ERR_BAD_SHAPE;
+    if (ws_bytes < flexq_linear_workspace_bytes(M, K) || ((uintptr_t)ws & 255)) return FLEXQ_ERR_WORKSPACE;
+    uint8_t* base = reinterpret_cast<uint8_t*>(ws) + flexq_gemm_workspace_bytes();
+    *xq = reinterpret_cast<int8_t*>(base);
+    *sx = reinterpret_cast<float*>(base + align_up((size_t)M * K, 256));
+    return 0;
+}
+
+int flexq_linear_w6ax_f16(const void* x, const uint8_t* w6, const void* w_scale, void* d, int M, int N, int K, int x_bits,
+                          int mode, void* ws, size_t ws_bytes, void* stream) {
+    int8_t* xq; float* sx;
+    if (int e = carve(ws, ws_bytes, M, K, &xq, &sx)) return e;
+    if (int e = quant_act_native((const __half*)x, xq, sx, M, K, x_bits, mode, (cudaStream_t)stream)) return e;
+    return gemm_w6ax(xq, sx, w6, (const __half*)w_scale, (__half*)d, M, N, K, ws, flexq_gemm_workspace_bytes(), (cudaStream_t)stream);
+}
+
+int flexq_gemm_ref_layout(const int32_t* x_planes, const void* x_scale, const uint8_t* w6, const void* w_scale, void* d,
+                          int M, int N, int K, int x_bits, void* ws, size_t ws_bytes, void* stream) {
+    int8_t* xq; float* sx;
+    if (x_bits != 6 && x_bits != 8) return FLEXQ_ERR_BAD_BITS;
+    if (int e = carve(ws, ws_bytes, M, K, &xq, &sx)) return e;
+    if (int e = planes_to_i8(reinterpret_cast<const uint32_t*>(x_planes), xq, M, K, x_bits, (cudaStream_t)stream)) return e;
+    if (int e = xscale_ref_to_sx((const __half*)x_scale, sx, M, K, (cudaStream_t)stream)) return e;
+    return gemm_w6ax(xq, sx, w6, (const __half*)w_scale, (__half*)d, M, N, K, ws, flexq_gemm_workspace_bytes(), (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+/*
+ * flexq_b200 -- C ABI of the B200-native (sm_100a) W6Ax quantized-linear hot path.
+ *
+ * This header is the drop-in boundary.  Every entry point takes plain device pointers,
+ * sizes and an opaque CUDA stream (a cudaStream_t passed as void*), returns an int status
+ * (0 = OK, <0 = FLEXQ_ERR_*, >0 = cudaError_t of the failing CUDA call) and never
+ * allocates, synchronises or falls back to the CPU.  Each declaration cites the
+ * reference (hoffmann-muki/FlexQ, paths under /root/reference) interface it replaces.
+ *
+ * Data formats (details: DESIGN.md "Data layout in HBM")
+ *   Xq      int8  [M][K]            quantised activations in int8 containers (A6 or A8)
+ *   sx      f32   [K/128][ldsx]     activation scales, ldsx = flexq_sx_ld(M); value is the
+ *                                   fp16-rounded scale the quantiser divided by
+ *   W6      u8    [ceil(N/128)][K/128][12288]  6-bit weights, 128x128 tiles, TMA-bulk friendly
+ *   w_scale f16   [K/128][N]        same as the reference's W_SCALE (test_bgemm_kernel.cu:57-63)
+ *   D       f16   [M][N]            row major, as the reference
+ *   planes  u32   [K/128][R/chunk][bits][chunk][4]   reference bit-plane layout
+ *                                   (engine/src/pack/bit_packing.cu:42-99), chunk = min(R,8)
+ *   X_SCALE f16   [K/128][2*ceil4(M)]  reference activation-scale layout, entries duplicated
+ *                                   in pairs (engine/test_bgemm_kernel.cu:41-54)
+ */
+#ifndef FLEXQ_B200_H_
+#define FLEXQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLEXQ_OK                 0
+#define FLEXQ_ERR_BAD_SHAPE     -1   /* K % 128 != 0, K < 128, M/N <= 0, plane layout needs R % min(R,8) == 0 */
+#define FLEXQ_ERR_BAD_BITS      -2   /* x_bits not in {6,8} (weights are always 6 bit)   */
+#define FLEXQ_ERR_NULL          -3
+#define FLEXQ_ERR_WORKSPACE     -4   /* workspace too small / misaligned                  */
+#define FLEXQ_ERR_NO_DEVICE     -5   /* no sm_100 device, or driver lacks cuTensorMapEncodeTiled */
+#define FLEXQ_ERR_TENSORMAP     -6
+
+#define FLEXQ_GROUP              128 /* engine/src/bgemm/flexq_bmma_kernel.h:54 */
+
+/* activation rounding behaviour -- the reference has two */
+#define FLEXQ_ROUND_CUDA         0   /* e2e/.../flexqgemm/src/pack/bit_packing.cu:150-163: fp16-rounded
+                                        scale, no min clamp, round half away from zero             */
+#define FLEXQ_ROUND_PYTHON       1   /* algorithm/flexq_quantize/quantizer.py:112-116,153-155: scale
+                                        clamped to [1e-5,1e4], round half to even, fp16 arithmetic  */
+
+int         flexq_version(void);
+const char* flexq_status_string(int status);
+
+/* ---- sizes ---------------------------------------------------------------------------- */
+size_t flexq_w6_packed_bytes(int N, int K);            /* 12288 * ceil(N/128) * K/128           */
+size_t flexq_planes_bytes(int R, int K, int bits);     /* R*K*bits/8, as the reference allocates  */
+int    flexq_sx_ld(int M);                             /* leading dim of sx: ceil4(M)             */
+size_t flexq_xscale_ref_halves(int M, int K);          /* K/128 * 2*ceil4(M)                      */
+size_t flexq_gemm_workspace_bytes(void);               /* split-K scratch, shape independent      */
+size_t flexq_linear_workspace_bytes(int M, int K);     /* gemm workspace + Xq + sx                */
+
+/* Zero a workspace once after allocation (the GEMM leaves it zeroed again after every call).
+ * One workspace must not be shared by GEMMs running concurrently on different streams. */
+int flexq_workspace_init(void* workspace, size_t bytes, void* stream);
+
+/* ---- reference-layout packers (API parity) ------------------------------------------------
+ * replaces: cudaError_t flexq_bit_packing(const int*, int*, int M, int K, int BIT, cudaStream_t)
+ *           engine/src/pack/bit_packing.h:34 (kernel bit_packing.cu:42-99, launch :113-122)     */
+int flexq_bit_packing_i32(const int32_t* in, int32_t* planes, int R, int K, int bits, void* stream);
+
+/* replaces: void flexq_bit_packing(const half*, int*, half* T_out_scale, int M, int K, int BIT,
+ *           cudaStream_t)  e2e/src/fastertransformer/kernels/flexqgemm/src/pack/bit_packing.h:34
+ *           (kernel bit_packing.cu:80-199): per-(row,group) absmax -> scale -> quantise -> planes,
+ *           scales written twice as half at [g][2m], [g][2m+1].                                 */
+int flexq_bit_packing_f16(const void* x_half, int32_t* planes, void* x_scale_half,
+                          int M, int K, int bits, void* stream);
+
+/* ---- native activation path (north-star subsystem 2) -------------------------------------
+ * Fused per-token per-group absmax -> 6/8-bit quantise -> int8 containers + fp32 scales.
+ * Same arithmetic as flexq_bit_packing_f16 (mode FLEXQ_ROUND_CUDA) or as
+ * UniformAffineQuantizer (mode FLEXQ_ROUND_PYTHON).                                            */
+int flexq_quant_act(const void* x_half, int8_t* xq, float* sx, int M, int K, int bits, int mode,
+                    void* stream);
+
+/* ---- offline weight packer (north-star subsystem 1) --------------------------------------
+ * ints [N][K] (two's complement in 6 bits, i.e. [-32,31]; int32 or int8 input) -> W6 tiles.
+ * Caller of the int32 form today: engine/test_bgemm_kernel.cu:222-224 (flexq_bit_packing on W). */
+int flexq_pack_w6_i32(const int32_t* w_int, uint8_t* w6, int N, int K, void* stream);
+int flexq_pack_w6_i8(const int8_t* w_int, uint8_t* w6, int N, int K, void* stream);
+
+/* fp16 / fp32 weights [N][K] -> per-group symmetric 6-bit quantisation exactly as
+ * UniformAffineQuantizer does for weights (quantizer.py:144-171 + 93-126, arithmetic in the
+ * input dtype) -> W6 tiles + w_scale f16 [K/128][N].  This is the exporter the reference lacks
+ * (flexq_quantize/utils.py:116-123 only overwrites W with its fake-quantised value).            */
+int flexq_quant_pack_w6_f16(const void* w_half, uint8_t* w6, void* w_scale_half, int N, int K, void* stream);
+int flexq_quant_pack_w6_f32(const float* w, uint8_t* w6, void* w_scale_half, int N, int K, void* stream);
+
+/* ---- converters from the reference layouts -------------------------------------------------- */
+int flexq_planes_to_i8(const int32_t* planes, int8_t* out, int R, int K, int bits, void* stream);
+int flexq_planes_to_w6(const int32_t* w_planes, uint8_t* w6, int8_t* scratch_NK, int N, int K, void* stream);
+int flexq_xscale_ref_to_sx(const void* x_scale_half, float* sx, int M, int K, void* stream);
+int flexq_w6_to_i8(const uint8_t* w6, int8_t* out, int N, int K, void* stream);   /* unpack (debug/tests) */
+
+/* ---- W6A6 / W6A8 GEMM (north-star subsystem 3) -------------------------------------------
+ * D[m][n] = half( sum_g sx[g][m] * float(w_scale[g][n]) * S[m][n][g] ),
+ * S[m][n][g] = sum_{k in group g} Xq[m][k] * W[n][k]   (INT32, exact; tcgen05.mma kind::i8).
+ * replaces: FQBMMAInitFn_t / FQBMMAExecFn_t pairs  engine/src/bgemm/flexq_bmma_op.h:163-188
+ *           (kernel flexq_bmma_kernel.h:119-447) and FLEXQGEMMWrapper::gemm(int* A ...)
+ *           e2e/.../flexqgemm/flexq_gemm_wrapper.cu:21-97.                                       */
+int flexq_gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale_half,
+                    void* d_half, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* Debug/parity entry: the INT32 per-K-group partial sums S[M][N][K/128] of the same kernel. */
+int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K,
+                              void* stream);
+
+/* Fused linear: fp16 activations in, fp16 out (activation quantise + GEMM on one stream).
+ * replaces: FLEXQGEMMWrapper::gemm(half* A ...) flexq_gemm_wrapper.cu:99-122 and is what
+ * QuantLinear.forward (algorithm/flexq_quantize/int_linear.py:56-72) maps to.                   */
+int flexq_linear_w6ax_f16(const void* x_half, const uint8_t* w6, const void* w_scale_half, void* d_half,
+                          int M, int N, int K, int x_bits, int mode, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Engine-level drop-in on the reference's own operand layouts: X as bit planes + duplicated
+ * half scales (what flexq_bit_packing / the FT layers produce), W already converted once with
+ * flexq_planes_to_w6.  Workspace as flexq_linear_workspace_bytes(M, K).                          */
+int flexq_gemm_ref_layout(const int32_t* x_planes, const void* x_scale_half, const uint8_t* w6,
+                          const void* w_scale_half, void* d_half, int M, int N, int K, int x_bits,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEXQ_B200_H_ */

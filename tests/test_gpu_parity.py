@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar: bit-exact for every integer/byte result (quantised ints, packed words, INT32 group
+sums); fp16 outputs within a stated tolerance of (a) the exact real value of the kernel's
+formula and (b) the reference's fake-quant path.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# FP16 output tolerance: rms-relative <= 1e-3, max-abs <= 1e-2 * mean|ref|
+RMS_REL_TOL = 1e-3
+MAXABS_REL_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from flexq_b200 import capi as c
+    c.load()
+    assert torch.cuda.is_available()
+    return c
+
+
+def _rand_case(rng, M, N, K, xb):
+    xq = rng.integers(-(1 << (xb - 1)), 1 << (xb - 1), size=(M, K)).astype(np.int8)
+    wq = rng.integers(-32, 32, size=(N, K)).astype(np.int8)
+    sx = (rng.random((M, K // 128)) * 0.1 + 1e-3).astype(np.float16)
+    sw = (rng.random((K // 128, N)) * 0.1 + 1e-3).astype(np.float16)
+    return xq, wq, sx, sw
+
+
+def _sx_dev(capi, sx_h, M, G):
+    sxf = np.zeros((G, capi.ceil4(M)), dtype=np.float32)
+    sxf[:, :M] = sx_h.astype(np.float32).T
+    return torch.from_numpy(sxf).cuda()
+
+
+def _check_close(out, ref):
+    out = out.astype(np.float64)
+    ref = ref.astype(np.float64)
+    rms = np.sqrt(np.mean((out - ref) ** 2)) / max(np.sqrt(np.mean(ref ** 2)), 1e-30)
+    mx = np.abs(out - ref).max() / max(np.abs(ref).mean(), 1e-30)
+    assert rms <= RMS_REL_TOL and mx <= MAXABS_REL_TOL, (rms, mx)
+
+
+# ------------------------------------------------------------------------------------------
+# packers / converters: byte exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K", [(128, 128), (200, 384), (384, 1024), (8, 128)])
+def test_pack_w6_matches_oracle_layout(capi, oracle, N, K):
+    rng = np.random.default_rng(N * 7 + K)
+    wq = rng.integers(-32, 32, size=(N, K)).astype(np.int32)
+    ref = oracle.pack_w6_native(wq)
+    for dt in (torch.int32, torch.int8):
+        w6 = capi.pack_w6(torch.from_numpy(wq).to(dt).cuda())
+        assert np.array_equal(w6.cpu().numpy().reshape(ref.shape), ref)
+    back = capi.w6_to_i8(w6, N, K).cpu().numpy()
+    assert np.array_equal(back.astype(np.int32), wq)
+
+
+@pytest.mark.parametrize("R,K,bits", [(1, 128, 6), (2, 256, 8), (4, 512, 6), (8, 384, 8), (16, 256, 6), (64, 1024, 6)])
+def test_bit_packing_i32_matches_reference_layout(capi, oracle, R, K, bits):
+    rng = np.random.default_rng(R + K + bits)
+    raw = rng.integers(0, 1 << bits, size=(R, K)).astype(np.int32)      # as the harness draws them
+    planes = capi.bit_packing_i32(torch.from_numpy(raw).cuda(), bits).cpu().numpy().view(np.uint32)
+    assert np.array_equal(planes, oracle.pack_planes(raw, bits))
+    ints = capi.planes_to_i8(torch.from_numpy(planes.view(np.int32)).cuda(), R, K, bits).cpu().numpy()
+    assert np.array_equal(ints.astype(np.int32), oracle.to_twos_complement_range(raw, bits))
+
+
+@pytest.mark.parametrize("N,K", [(128, 256), (264, 384)])
+def test_planes_to_w6(capi, oracle, N, K):
+    rng = np.random.default_rng(5)
+    wq = rng.integers(-32, 32, size=(N, K)).astype(np.int32)
+    planes = oracle.pack_planes(wq, 6).view(np.int32)
+    w6 = capi.planes_to_w6(torch.from_numpy(planes).cuda(), N, K).cpu().numpy()
+    assert np.array_equal(w6.reshape(-1), oracle.pack_w6_native(wq).reshape(-1))
+
+
+# ------------------------------------------------------------------------------------------
+# activation quantiser: ints and scales bit exact in both rounding modes
+# ------------------------------------------------------------------------------------------
+def _act_inputs(rng, M, K):
+    x = rng.standard_normal((M, K)).astype(np.float16)
+    if M >= 4:
+        x[0, :128] = 0                          # all-zero group (0/0 in the reference kernel)
+        x[1, :128] = np.float16(1e-7)           # scale underflows in half
+        x[2, :128] = (np.arange(128) - 63.5).astype(np.float16)   # ties
+        x[3, 5] = 300.0
+    return x
+
+
+@pytest.mark.parametrize("M,K,bits", [(1, 128, 6), (5, 384, 6), (16, 4096, 6), (16, 4096, 8), (33, 1024, 8)])
+def test_quant_act_cuda_mode(capi, oracle, M, K, bits):
+    x = _act_inputs(np.random.default_rng(M + bits), M, K)
+    q_ref, s_ref = oracle.quant_act_cuda(x, bits)
+    xq, sx = capi.quant_act(torch.from_numpy(x).cuda(), bits, capi.ROUND_CUDA)
+    assert np.array_equal(xq.cpu().numpy().astype(np.int32), q_ref)
+    sx = sx.cpu().numpy()
+    assert np.array_equal(sx[:, :M].T, s_ref.astype(np.float32))
+    assert np.all(sx[:, M:] == 0)
+
+
+@pytest.mark.parametrize("M,K,bits", [(5, 384, 6), (16, 1024, 8)])
+def test_quant_act_python_mode(capi, oracle, M, K, bits):
+    x = _act_inputs(np.random.default_rng(M + bits), M, K)
+    q_ref, s_ref, _ = oracle.quant_sym_python(x, bits)
+    xq, sx = capi.quant_act(torch.from_numpy(x).cuda(), bits, capi.ROUND_PYTHON)
+    assert np.array_equal(xq.cpu().numpy().astype(np.int32), q_ref)
+    assert np.array_equal(sx.cpu().numpy()[:, :M].T, s_ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("M,K,bits", [(1, 128, 6), (4, 384, 8), (8, 1024, 6), (16, 512, 6)])
+def test_bit_packing_f16_reference_layout(capi, oracle, M, K, bits):
+    x = _act_inputs(np.random.default_rng(M), M, K)
+    q_ref, s_ref = oracle.quant_act_cuda(x, bits)
+    planes, xs = capi.bit_packing_f16(torch.from_numpy(x).cuda(), bits)
+    assert np.array_equal(planes.cpu().numpy().view(np.uint32), oracle.pack_planes(q_ref, bits))
+    assert np.array_equal(xs.cpu().numpy(), oracle.x_scale_layout(s_ref))
+
+
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+def test_quant_pack_w6(capi, oracle, dtype):
+    rng = np.random.default_rng(11)
+    N, K = 200, 512
+    w = (0.02 * rng.standard_normal((N, K))).astype(dtype)
+    w[0, :128] = 0
+    q_ref, s_ref, _ = oracle.quant_sym_python(w, 6)
+    w6, ws = capi.quant_pack_w6(torch.from_numpy(w).cuda())
+    assert np.array_equal(capi.w6_to_i8(w6, N, K).cpu().numpy().astype(np.int32), q_ref)
+    assert np.array_equal(ws.cpu().numpy(), s_ref.T.astype(np.float16))
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM: INT32 group sums bit exact; fp16 output within tolerance
+# ------------------------------------------------------------------------------------------
+GEMM_SHAPES = [
+    (1, 128, 128, 6), (1, 256, 512, 8), (4, 128, 256, 6), (8, 384, 1024, 6), (16, 512, 4096, 6),
+    (16, 200, 384, 8),           # ragged N
+    (17, 256, 512, 6), (32, 256, 1024, 8), (33, 128, 256, 6), (64, 384, 512, 6),
+    (100, 256, 1024, 8), (128, 512, 512, 6), (300, 384, 2048, 6),
+]
+
+
+@pytest.mark.parametrize("M,N,K,xb", GEMM_SHAPES)
+def test_gemm_groupsums_bit_exact(capi, oracle, M, N, K, xb):
+    xq, wq, _, _ = _rand_case(np.random.default_rng(M * 3 + N + K), M, N, K, xb)
+    w6 = capi.pack_w6(torch.from_numpy(wq).cuda())
+    S = capi.gemm_w6ax_groupsums(torch.from_numpy(xq).cuda(), w6, N).cpu().numpy()
+    S_ref = oracle.group_sums(xq.astype(np.int32), wq.astype(np.int32))
+    assert np.array_equal(S, S_ref)
+
+
+@pytest.mark.parametrize("M,N,K,xb", GEMM_SHAPES)
+def test_gemm_fp16_output(capi, oracle, M, N, K, xb):
+    xq, wq, sx, sw = _rand_case(np.random.default_rng(M + N * 5 + K), M, N, K, xb)
+    w6 = capi.pack_w6(torch.from_numpy(wq).cuda())
+    ws = capi.new_workspace()
+    out = None
+    for _ in range(2):                     # twice: the split-K workspace must come back clean
+        out = capi.gemm_w6ax(torch.from_numpy(xq).cuda(), _sx_dev(capi, sx, M, K // 128), w6,
+                             torch.from_numpy(sw).cuda(), N, ws).cpu().numpy()
+    S = oracle.group_sums(xq.astype(np.int32), wq.astype(np.int32))
+    _check_close(out, oracle.gemm_exact(S, sx, sw))
+    _check_close(out, oracle.gemm_refkernel_numerics(S, sx, sw))
+    assert not ws.any().item(), "split-K workspace not restored to zero"
+
+
+def test_gemm_extreme_values(capi, oracle):
+    """all operands at their extreme: |S| = 128*128*32 per group stays exact"""
+    M, N, K = 16, 128, 256
+    xq = np.full((M, K), -128, dtype=np.int8)
+    wq = np.full((N, K), -32, dtype=np.int8)
+    wq[::2] = 31
+    w6 = capi.pack_w6(torch.from_numpy(wq).cuda())
+    S = capi.gemm_w6ax_groupsums(torch.from_numpy(xq).cuda(), w6, N).cpu().numpy()
+    assert np.array_equal(S, oracle.group_sums(xq.astype(np.int32), wq.astype(np.int32)))
+
+
+@pytest.mark.parametrize("M,N,K,xb", [(16, 4096, 4096, 6), (8, 1024, 2048, 8), (128, 1024, 1024, 6)])
+def test_linear_vs_fakequant(capi, oracle, M, N, K, xb):
+    """Fused fp16 linear vs the reference's fake-quant path (oracle.fakequant_linear is pinned to
+    the reference's QuantLinear by tests/golden)."""
+    rng = np.random.default_rng(1)
+    w = (0.02 * rng.standard_normal((N, K))).astype(np.float16)
+    x = rng.standard_normal((M, K)).astype(np.float16)
+    w6, wsc = capi.quant_pack_w6(torch.from_numpy(w).cuda())
+    ws = capi.new_workspace(M, K)
+    y = capi.linear_w6ax(torch.from_numpy(x).cuda(), w6, wsc, N, xb, ws, capi.ROUND_PYTHON).cpu().numpy()
+    ref = oracle.fakequant_linear(x.astype(np.float32), w.astype(np.float32), 6, xb)
+    # same integers? fp16 vs fp32 quantiser arithmetic can flip a rare tie, so compare values
+    out = y.astype(np.float64)
+    r = ref.astype(np.float64)
+    rms = np.sqrt(np.mean((out - r) ** 2)) / np.sqrt(np.mean(r ** 2))
+    assert rms <= 5e-3, rms
+
+
+def test_gemm_ref_layout_dropin(capi, oracle):
+    """engine-level drop-in: X as reference bit planes + duplicated half scales"""
+    M, N, K, xb = 8, 256, 512, 6
+    xq, wq, sx, sw = _rand_case(np.random.default_rng(3), M, N, K, xb)
+    xp = torch.from_numpy(oracle.pack_planes(xq.astype(np.int32), xb).view(np.int32)).cuda()
+    xs = torch.from_numpy(oracle.x_scale_layout(sx)).cuda()
+    w6 = capi.planes_to_w6(torch.from_numpy(oracle.pack_planes(wq.astype(np.int32), 6).view(np.int32)).cuda(), N, K)
+    ws = capi.new_workspace(M, K)
+    out = capi.gemm_ref_layout(xp, xs, w6, torch.from_numpy(sw).cuda(), M, N, K, xb, ws).cpu().numpy()
+    S = oracle.group_sums(xq.astype(np.int32), wq.astype(np.int32))
+    _check_close(out, oracle.gemm_exact(S, sx, sw))
