@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""Benchmark of the W6Ax quantized-linear hot path on B200 (contract: see DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): the LLaMA-2-70B
+linear layers 8192x8192, 28672x8192, 8192x28672 (N x K), W6A6, prefill M = 2048, synthetic
+random-init fp16 weights and activations.  One step = one pass of the fused path
+(dynamic activation quantise -> W6A6 tcgen05 GEMM -> fp16) over the three layers.
+With --gpus N > 1 the same layers are tensor-parallel over N ranks (o_proj-like 8192x8192 and
+down 8192x28672 row-parallel with an NCCL all-reduce, gate/up 28672x8192 column-parallel), i.e.
+strong scaling.  Metric: TOPS = 2*M*N*K summed over the layers / time (the reference harness's
+definition, engine/test/test_w6a6_kernel.cu:36-37).
+
+`--impl reference` times the reference's own CPU implementation of the path (the fake-quant
+QuantLinear, restated in oracle/fakequant_torch.py because /root/reference does not travel to
+the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_TOKENS = 2048
+# (name, N, K, tensor-parallel mode, activation bits)
+LAYERS = [("attn_o_8192x8192", 8192, 8192, "row", 6),
+          ("mlp_gate_28672x8192", 28672, 8192, "column", 6),
+          ("mlp_down_8192x28672", 8192, 28672, "row", 6)]
+WORKLOAD = "llama2-70b linears {8192x8192, 28672x8192, 8192x28672} W6A6 g128 prefill M=2048"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU fake-quant path on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, sample_rows: int):
+    from oracle.fakequant_torch import FakeQuantLinearCPU      # baseline leg: the only oracle use here
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    mods, xs = [], []
+    for _, N, K, _, ab in LAYERS:
+        mods.append(FakeQuantLinearCPU(0.02 * torch.randn(N, K, generator=g), ab, faithful=True))
+        xs.append(torch.randn(sample_rows, K, generator=g))
+    ops = sum(2.0 * sample_rows * N * K for _, N, K, _, _ in LAYERS)
+    for _ in range(warmup):
+        for m, x in zip(mods, xs):
+            m(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for m, x in zip(mods, xs):
+            m(x)
+    dt = (time.perf_counter() - t0) / steps
+    sample = (f"{sample_rows} of {M_TOKENS} token rows through all three layers, fp32, weights re-fake-quantised every "
+              f"forward as the reference does (int_linear.py:60-62); {steps} steps")
+    return ops / dt / 1e12, dt * 1e3, cores, sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    tops, ms, cores, sample = cpu_reference_run(steps, warmup, sample_rows=32)
+    line = {"impl": "reference", "metric": "W6A6 GEMM TOPS (2*M*N*K/t), llama2-70b linear layers", "value": tops,
+            "unit": "TOPS", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arm": "reference CPU fake-quant path (oracle port)"},
+            "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="flexq_b200", choices=["flexq_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from flexq_b200 import capi, tp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    capi.load()
+
+    # ---- build the (sharded) layers: synthetic random-init weights, packed offline on the GPU
+    torch.manual_seed(1234)
+    layers, x_dev, x_host, y_host = [], [], [], []
+    for name, N, K, mode, ab in LAYERS:
+        Nl, Kl = (N // world, K) if mode == "column" else (N, K // world)
+        w = (0.02 * torch.randn(Nl, Kl, device=dev)).half()
+        w6, wsc = capi.quant_pack_w6(w)
+        del w
+        lin = tp.TPLinearW6Ax.from_packed(w6, wsc, Nl, Kl, mode, ab, rank, world)
+        layers.append(lin)
+        x = torch.randn(M_TOKENS, Kl, device=dev).half()
+        x_dev.append(x)
+        x_host.append(x.cpu().pin_memory())
+        y_host.append(torch.empty(M_TOKENS, Nl, dtype=torch.float16).pin_memory())
+    outs = [torch.empty(M_TOKENS, l.N, dtype=torch.float16, device=dev) for l in layers]
+    total_ops = sum(2.0 * M_TOKENS * N * K for _, N, K, _, _ in LAYERS)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        for lin, x, o in zip(layers, x_dev, outs):
+            lin.forward(x, o)
+
+    def step_e2e():
+        for lin, xh, yh, o in zip(layers, x_host, y_host, outs):
+            xd = xh.to(dev, non_blocking=True)
+            lin.forward(xd, o)
+            yh.copy_(o, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, max(3, args.steps // 4), 2)
+
+    # ---- dominant kernel (the W6A6 GEMM) timed alone on pre-quantised operands -> roofline
+    roof = None
+    if rank == 0 or world > 1:
+        pre = []
+        for lin, x in zip(layers, x_dev):
+            xq, sx = capi.quant_act(x, lin.x_bits, capi.ROUND_CUDA)
+            pre.append((xq, sx))
+        gws = capi.new_workspace()
+
+        def gemm_only():
+            for lin, (xq, sx), o in zip(layers, pre, outs):
+                capi.gemm_w6ax(xq, sx, lin.w6, lin.w_scale, lin.N, gws, o)
+
+        ms_gemm = timed(gemm_only, args.steps, 3)
+        _, bf16_tf, src = peaks()
+        peak = 2.0 * bf16_tf                       # kind::i8 issues at twice the bf16 rate on sm_100
+        achieved = total_ops / world / (ms_gemm * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOPS", "frac": achieved / peak,
+                "traffic": None, "kernel": "w6ax_gemm_kernel<128>", "launches_per_step": len(LAYERS),
+                "avg_launch_ms": ms_gemm / len(LAYERS),
+                "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({src}); int8 dense = 2x bf16 dense on sm_100"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        tops, _, cores, sample = cpu_reference_run(steps=2, warmup=1, sample_rows=32)
+        cpu = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample}
+
+    h2d = sum(x.numel() * 2 for x in x_host)
+    d2h = sum(y.numel() * 2 for y in y_host)
+    line = {
+        "metric": "W6A6 GEMM TOPS (2*M*N*K/t), llama2-70b linear layers", "value": total_ops / (ms_step * 1e-3) / 1e12,
+        "unit": "TOPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tokens": M_TOKENS, "parallelism": f"tp{world}",
+                   "l2": "per-step working set (384 MB packed weights + activations) exceeds the 126 MB L2",
+                   "step": "fused activation quantise + W6A6 GEMM per layer" + (" + NCCL all-reduce on row-parallel layers" if world > 1 else "")},
+        "e2e": {"value": total_ops / (ms_e2e * 1e-3) / 1e12, "unit": "TOPS", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": 2 * len(LAYERS) * args.steps,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

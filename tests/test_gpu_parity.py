@@ -189,12 +189,14 @@ def test_linear_vs_fakequant(capi, oracle, M, N, K, xb):
     w6, wsc = capi.quant_pack_w6(torch.from_numpy(w).cuda())
     ws = capi.new_workspace(M, K)
     y = capi.linear_w6ax(torch.from_numpy(x).cuda(), w6, wsc, N, xb, ws, capi.ROUND_PYTHON).cpu().numpy()
-    ref = oracle.fakequant_linear(x.astype(np.float32), w.astype(np.float32), 6, xb)
-    # same integers? fp16 vs fp32 quantiser arithmetic can flip a rare tie, so compare values
-    out = y.astype(np.float64)
-    r = ref.astype(np.float64)
-    rms = np.sqrt(np.mean((out - r) ** 2)) / np.sqrt(np.mean(r ** 2))
-    assert rms <= 5e-3, rms
+    # the reference runs fp16 models with fp16 quantiser arithmetic (quantizer.py works in x.dtype):
+    # same integers and scales as the kernel path, so only fp accumulation/rounding differs
+    ref = oracle.fakequant_linear(x, w, 6, xb)
+    _check_close(y, ref)
+    # a6 (CUDA) rounding differs from the python path only at ties / via the missing scale clamp
+    y2 = capi.linear_w6ax(torch.from_numpy(x).cuda(), w6, wsc, N, xb, ws, capi.ROUND_CUDA).cpu().numpy()
+    out, r = y2.astype(np.float64), ref.astype(np.float64)
+    assert np.sqrt(np.mean((out - r) ** 2)) / np.sqrt(np.mean(r ** 2)) <= 1e-2
 
 
 def test_gemm_ref_layout_dropin(capi, oracle):

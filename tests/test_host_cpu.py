@@ -1,0 +1,148 @@
+"""CPU tests of the host side: C ABI surface, python mirrors of the reference modules, TP logic
+over gloo (world_size 2).  No compute calls into the CUDA library here."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_capi_library_exports_every_header_symbol():
+    from flexq_b200 import capi
+    lib = capi.load()
+    hdr = open(os.path.join(ROOT, "include", "flexq_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(flexq_[a-z0-9_]+)\s*\(", hdr, flags=re.M))
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    # size helpers are host-only arithmetic
+    assert lib.flexq_w6_packed_bytes(8192, 8192) == 8192 * 8192 * 6 // 8
+    assert lib.flexq_w6_packed_bytes(200, 256) == 2 * 2 * 12288
+    assert lib.flexq_planes_bytes(16, 4096, 6) == 16 * 4096 * 6 // 8
+    assert lib.flexq_sx_ld(5) == 8 and lib.flexq_xscale_ref_halves(5, 256) == 2 * 16
+    assert lib.flexq_status_string(-1).decode().startswith("bad shape")
+    assert lib.flexq_version() >= 100
+
+
+def test_capi_argument_validation_without_gpu():
+    """error behaviour: status codes, not printf (reference: flexq_gemm_wrapper.cu:43-46)"""
+    from flexq_b200 import capi
+    lib = capi.load()
+    assert lib.flexq_gemm_w6ax(None, None, None, None, None, 1, 128, 128, None, 0, None) == -3
+    one = ctypes.c_void_p(16)
+    assert lib.flexq_gemm_w6ax(one, one, one, one, one, 1, 128, 100, one, 1 << 30, None) == -1    # K % 128
+    assert lib.flexq_gemm_w6ax(one, one, one, one, one, 1, 128, 128, one, 16, None) == -4         # workspace
+    assert lib.flexq_quant_act(one, one, one, 4, 256, 7, 0, None) == -2                           # bits
+    assert lib.flexq_bit_packing_i32(one, one, 12, 128, 6, None) == -1                            # ragged planes
+
+
+def _params(bits, axes):
+    return dict(n_bits=bits, per_channel_axes=axes, symmetric=True, dynamic_method="per_group",
+                group_size=128, disable_zero_point=True)
+
+
+def test_quantizer_mirror_matches_reference_golden():
+    from flexq_b200 import UniformAffineQuantizer
+    g = np.load(os.path.join(ROOT, "tests", "golden", "quantizer_golden.npz"))
+    for n in sorted({k.split("/")[0] for k in g.files}):
+        x = torch.from_numpy(g[n + "/x"])
+        q = UniformAffineQuantizer(**_params(int(g[n + "/bits"]), []))
+        d = q(x.clone())
+        assert torch.equal(d, torch.from_numpy(g[n + "/deq"])), n
+        assert torch.equal(q.scale.reshape(x.shape[0], -1), torch.from_numpy(g[n + "/scale"])), n
+        assert q.is_flexq_kernel_config()
+
+
+def test_quantlinear_mirror_api_and_fake_mode():
+    from flexq_b200 import QuantLinear, capi
+    g = np.load(os.path.join(ROOT, "tests", "golden", "linear_golden.npz"))
+    lin = nn.Linear(256, 40, bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(g["lin_w6a6_f32/w"]))
+    ql = QuantLinear(lin, _params(6, [0]), _params(6, []), fake_quant_fallback=True)
+    for attr in ("weight", "bias", "in_features", "out_features", "use_weight_quant", "use_act_quant",
+                 "weight_quantizer", "act_quantizer", "use_temporary_parameter", "set_quant_state"):
+        assert hasattr(ql, attr)
+    x = torch.from_numpy(g["lin_w6a6_f32/x"])
+    assert torch.equal(ql(x), lin(x))                         # quant state off == plain linear
+    ql.set_quant_state(True, True)
+    assert ql.kernel_supported()
+    # on CPU the real-quant path refuses to run (no CPU fallback) ...
+    with pytest.raises(capi.FlexQError):
+        ql(x)
+    # ... while the explicit fake-quant evaluation mode reproduces the reference bit for bit
+    ql.set_quant_state(True, False)
+    ql2 = QuantLinear(lin, _params(6, [0]), _params(6, []), fake_quant_fallback=True)
+    ql2.set_quant_state(True, True)
+    y = ql2._forward_fake(x)
+    assert torch.allclose(y, torch.from_numpy(g["lin_w6a6_f32/y"]), rtol=0, atol=2e-6 * float(y.abs().mean()) + 1e-7)
+
+
+def test_quantlinear_unsupported_config_raises():
+    from flexq_b200 import QuantLinear, capi
+    lin = nn.Linear(256, 16, bias=False)
+    p = _params(4, [0])
+    ql = QuantLinear(lin, p, _params(6, []))
+    ql.set_quant_state(True, True)
+    assert not ql.kernel_supported()
+    with pytest.raises(capi.FlexQError):
+        ql(torch.randn(2, 256))
+
+
+# ---- tensor parallel host logic over gloo ----------------------------------------------------------
+def _tp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from flexq_b200 import tp
+    torch.manual_seed(0)
+    N, K, M = 512, 1024, 4
+    w = torch.randn(N, K)
+    x = torch.randn(M, K)
+    full = x @ w.t()
+    # column parallel: shard rows of W; outputs concatenate, no communication
+    wc = tp.shard_weight(w, "column", rank, world)
+    assert wc.shape == (N // world, K)
+    yc = x @ wc.t()
+    gathered = [torch.zeros_like(yc) for _ in range(world)]
+    dist.all_gather(gathered, yc)
+    ok_col = torch.allclose(torch.cat(gathered, dim=1), full, atol=1e-4)
+    # row parallel: shard K on 128-group boundaries; partial sums all-reduced
+    wr = tp.shard_weight(w, "row", rank, world)
+    xr = tp.shard_activation(x, rank, world)
+    assert wr.shape == (N, K // world) and xr.shape == (M, K // world) and (K // world) % 128 == 0
+    yr = tp.all_reduce_sum(xr @ wr.t())
+    ok_row = torch.allclose(yr, full, atol=1e-3)
+    q.put((rank, ok_col, ok_row))
+    dist.destroy_process_group()
+
+
+def test_tp_sharding_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_tp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok_c and ok_r for _, ok_c, ok_r in res), res
+
+
+def test_tp_shard_validation():
+    from flexq_b200 import tp
+    w = torch.zeros(512, 1024)
+    with pytest.raises(ValueError):
+        tp.shard_weight(w, "row", 0, 3)          # K/128 = 8 groups not divisible by 3
+    with pytest.raises(ValueError):
+        tp.shard_weight(w, "diag", 0, 2)
