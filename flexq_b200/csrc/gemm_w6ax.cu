@@ -20,6 +20,7 @@
 // Warp roles (512 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 4-7 = weight expanders (6 bit -> int8, swizzled UMMA layout), warps 8-15 = epilogue.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -43,14 +44,15 @@ struct Cfg {
     static constexpr int NA = 3;                                   // expanded-weight stages (16 KB)
     static constexpr int NX = (M_TILE >= 256) ? 3 : 4;             // activation stages
     static constexpr int NW = (M_TILE >= 256) ? 4 : (M_TILE >= 128 ? 6 : 10);   // packed-weight stages (12 KB)
-    static constexpr int NS = 8;                                   // sx stages
+    static constexpr int NS = 8;                                   // scale stages (sx row + sw row)
+    static constexpr int S_BYTES = M_TILE * 4 + kTileN * 2;        // f32 sx[M_TILE] | f16 sw[128]
     static constexpr int X_BYTES = M_TILE * 128;
     static constexpr int A_BYTES = kTileN * 128;
     static constexpr int OFF_A = 0;
     static constexpr int OFF_X = OFF_A + NA * A_BYTES;
     static constexpr int OFF_W = OFF_X + NX * X_BYTES;
     static constexpr int OFF_S = OFF_W + NW * kTileBytes;
-    static constexpr int OFF_BAR = OFF_S + NS * M_TILE * 4;
+    static constexpr int OFF_BAR = OFF_S + NS * S_BYTES;
     static constexpr int NBAR = 2 * (NA + NX + NW + NS) + 4;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_MISC + 16 + 1024;        // + alignment slack
@@ -106,8 +108,12 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = misc[0];
 
+    // Register budget (64K regs, 512 threads): producer/MMA warpgroup 40, expanders 72, the two
+    // epilogue warpgroups 200 each (fp32 tile accumulators live in registers).
+    // (setmaxnreg sits inside each role branch so that ptxas allocates per role.)
     if (warp == 0) {
         // ===================== TMA producer =====================
+        reg_dealloc<40>();
         if (lane == 0) {
             int iw = 0, ix = 0, is = 0;
             for (int u = u_begin; u < u_end;) {
@@ -129,12 +135,15 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                         mbar_expect_tx(bar_x_full(s), C::X_BYTES);
                         tma_load_2d(smem_base + C::OFF_X + s * C::X_BYTES, &tmap_x, g * kGroup, m0, bar_x_full(s));
                     }
-                    if (!DUMP) {   // activation scales of this group
+                    if (!DUMP) {   // scales of this group: sx[g][m0..] (f32) and w_scale[g][n0..] (f16)
                         const int s = is % C::NS; const uint32_t ph = (is / C::NS) & 1; is++;
                         const int cols = min(M_TILE, p.ldsx - m0);
+                        const int rows = min(kTileN, p.N - nt * kTileN);
+                        const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
                         mbar_wait(bar_s_empty(s), ph ^ 1);
-                        mbar_expect_tx(bar_s_full(s), cols * 4);
-                        bulk_g2s(smem_base + C::OFF_S + s * M_TILE * 4, p.sx + (size_t)g * p.ldsx + m0, cols * 4, bar_s_full(s));
+                        mbar_expect_tx(bar_s_full(s), cols * 4 + rows * 2);
+                        bulk_g2s(dst, p.sx + (size_t)g * p.ldsx + m0, cols * 4, bar_s_full(s));
+                        bulk_g2s(dst + M_TILE * 4, p.w_scale + (size_t)g * p.N + nt * kTileN, rows * 2, bar_s_full(s));
                     }
                 }
                 u += g1 - g0;
@@ -143,13 +152,14 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        reg_dealloc<40>();
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
             const int n_units = u_end - u_begin;
             for (int i = 0; i < n_units; i++) {
                 const int buf = i & 1;
                 const int sa = i % C::NA, sx_ = i % C::NX;
-                mbar_wait(bar_acc_empty(buf), ((i >> 1) & 1) ^ 1);
+                mbar_wait(bar_acc_empty(buf), (i >> 1) & 1);      // armed (biased) by the epilogue warps
                 mbar_wait(bar_x_full(sx_), (i / C::NX) & 1);
                 mbar_wait(bar_a_full(sa), (i / C::NA) & 1);
                 tc_fence_after();
@@ -158,15 +168,18 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                 const uint32_t d_tmem = tmem_base + buf * M_TILE;
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    umma_i8(d_tmem, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc, k > 0);
+                    umma_i8(d_tmem, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc, 1u);
                 umma_commit(bar_x_empty(sx_));
                 umma_commit(bar_a_empty(sa));
                 umma_commit(bar_acc_full(buf));
             }
         }
         __syncwarp();
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp < 4) {
+        reg_dealloc<40>();                               // idle warps of warpgroup 0
+    } else if (warp < 8) {
         // ===================== weight expanders =====================
+        reg_dealloc<72>();
         const int r = threadIdx.x - 128;                 // weight row within the tile
         const int n_units = u_end - u_begin;
         for (int i = 0; i < n_units; i++) {
@@ -179,38 +192,56 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                 const uint4* src = reinterpret_cast<const uint4*>(wp + 48 * (128 * q + r));
                 in[q][0] = src[0]; in[q][1] = src[1]; in[q][2] = src[2];
             }
-            uint32_t out[2][4][4];
+            mbar_arrive(bar_w_empty(sw));                // packed tile fully in registers
+            mbar_wait(bar_a_empty(sa), ((i / C::NA) & 1) ^ 1);
+            uint8_t* arow = smem + C::OFF_A + sa * C::A_BYTES + r * 128;
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const uint32_t w[12] = {in[q][0].x, in[q][0].y, in[q][0].z, in[q][0].w, in[q][1].x, in[q][1].y,
                                         in[q][1].z, in[q][1].w, in[q][2].x, in[q][2].y, in[q][2].z, in[q][2].w};
 #pragma unroll
-                for (int s = 0; s < 4; s++) w6_expand16(w[3 * s], w[3 * s + 1], w[3 * s + 2], out[q][s]);
-            }
-            mbar_arrive(bar_w_empty(sw));                // packed tile fully in registers
-            mbar_wait(bar_a_empty(sa), ((i / C::NA) & 1) ^ 1);
-            uint8_t* arow = smem + C::OFF_A + sa * C::A_BYTES + r * 128;
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-#pragma unroll
                 for (int s = 0; s < 4; s++) {
+                    uint32_t o[4];
+                    w6_expand16(w[3 * s], w[3 * s + 1], w[3 * s + 2], o);
                     const int chunk = (4 * q + s) ^ (r & 7);     // 128-byte swizzle
-                    *reinterpret_cast<uint4*>(arow + 16 * chunk) = make_uint4(out[q][s][0], out[q][s][1], out[q][s][2], out[q][s][3]);
+                    *reinterpret_cast<uint4*>(arow + 16 * chunk) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+            }
             fence_proxy_async_smem();
             mbar_arrive(bar_a_full(sa));
         }
-    } else if (warp >= 8) {
+    } else {
         // ===================== epilogue =====================
+        reg_alloc<200>();
+        // Accumulators are re-armed with the bit pattern of 1.5*2^23 before every group, so the
+        // int32 sum 4*S read back from TMEM *is* the float (kMagicF + 4*S): one FMA with the
+        // per-row weight scale removes the bias exactly (kMagicF*sw is exact in fp32 for an
+        // fp16-valued sw) and a second FMA applies the per-token scale and accumulates.
         constexpr int CPT = C::CPT;
         constexpr int CH = CPT < 32 ? CPT : 32;          // columns per tcgen05.ld
+        constexpr uint32_t kMagicI = 0x4B400000u;
+        constexpr float kMagicF = 12582912.f;
         const int e = threadIdx.x - 256;
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
         const int half_id = e >> 7;
         const int r = quad * 32 + lane;
         const int col0 = half_id * CPT;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
-        float acc[CPT];
+        // arm both accumulator buffers once
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+#pragma unroll
+            for (int c = 0; c < CPT; c += (CPT < 16 ? 8 : 16)) {
+                if constexpr (CPT < 16) tmem_st8_same(t_lane + b * M_TILE + c, kMagicI);
+                else tmem_st16_same(t_lane + b * M_TILE + c, kMagicI);
+            }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_acc_empty(0));
+        mbar_arrive(bar_acc_empty(1));
+
+        float2 acc[CPT / 2];
         int i = 0, is = 0;
         for (int u = u_begin; u < u_end;) {
             const int tile = u / G, g0 = u - tile * G;
@@ -220,21 +251,24 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
             const int mbase = mt * M_TILE + col0;
             const bool n_ok = n < p.N;
 #pragma unroll
-            for (int j = 0; j < CPT; j++) acc[j] = 0.f;
+            for (int j = 0; j < CPT / 2; j++) acc[j] = make_float2(0.f, 0.f);
             for (int g = g0; g < g1; g++, i++) {
                 const int buf = i & 1;
-                float swv = 0.f;
-                if (!DUMP && n_ok) swv = 0.25f * __half2float(p.w_scale[(size_t)g * p.N + n]);   // operands hold 4*w
-                mbar_wait(bar_acc_full(buf), (i >> 1) & 1);
-                tc_fence_after();
+                float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
                 const float* sxs = nullptr;
                 int ss = 0;
                 if (!DUMP) {
                     ss = is % C::NS;
                     mbar_wait(bar_s_full(ss), (is / C::NS) & 1);
                     is++;
-                    sxs = reinterpret_cast<const float*>(smem + C::OFF_S + ss * M_TILE * 4) + col0;
+                    const uint8_t* st = smem + C::OFF_S + ss * C::S_BYTES;
+                    sxs = reinterpret_cast<const float*>(st) + col0;
+                    const float swv = n_ok ? 0.25f * __half2float(reinterpret_cast<const __half*>(st + M_TILE * 4)[r]) : 0.f;   // operands hold 4*w
+                    sw2 = make_float2(swv, swv);
+                    bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
                 }
+                mbar_wait(bar_acc_full(buf), (i >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < CPT; c += CH) {
                     uint32_t v[CH];
@@ -243,7 +277,14 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                     else if constexpr (CH == 16) tmem_ld16(ta, v);
                     else tmem_ld32(ta, v);
                     tmem_wait_ld();
-                    if (c + CH >= CPT) {                 // accumulator fully read: hand the buffer back
+                    // re-arm this chunk of the accumulator for its next group
+                    if constexpr (CH == 8) tmem_st8_same(ta, kMagicI);
+                    else {
+#pragma unroll
+                        for (int cc = 0; cc < CH; cc += 16) tmem_st16_same(ta + cc, kMagicI);
+                    }
+                    if (c + CH >= CPT) {                 // accumulator fully read and re-armed: hand it back
+                        tmem_wait_st();
                         tc_fence_before();
                         mbar_arrive(bar_acc_empty(buf));
                     }
@@ -252,17 +293,17 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
 #pragma unroll
                             for (int j = 0; j < CH; j++) {
                                 const int m = mbase + c + j;
-                                if (m < p.M) p.S[((size_t)m * p.N + n) * G + g] = ((int32_t)v[j]) >> 2;
+                                if (m < p.M) p.S[((size_t)m * p.N + n) * G + g] = ((int32_t)(v[j] - kMagicI)) >> 2;
                             }
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < CH; j += 4) {
                             const float4 s4 = *reinterpret_cast<const float4*>(sxs + c + j);
-                            acc[c + j + 0] = fmaf((float)(int32_t)v[j + 0] * swv, s4.x, acc[c + j + 0]);
-                            acc[c + j + 1] = fmaf((float)(int32_t)v[j + 1] * swv, s4.y, acc[c + j + 1]);
-                            acc[c + j + 2] = fmaf((float)(int32_t)v[j + 2] * swv, s4.z, acc[c + j + 2]);
-                            acc[c + j + 3] = fmaf((float)(int32_t)v[j + 3] * swv, s4.w, acc[c + j + 3]);
+                            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), sw2, bias2);
+                            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sw2, bias2);
+                            acc[(c + j) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c + j) / 2]);
+                            acc[(c + j) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c + j) / 2 + 1]);
                         }
                     }
                 }
@@ -275,7 +316,8 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
 #pragma unroll
                         for (int j = 0; j < CPT; j++) {
                             const int m = mbase + j;
-                            if (m < p.M) p.D[(size_t)m * p.N + n] = __float2half_rn(acc[j]);
+                            const float a = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
+                            if (m < p.M) p.D[(size_t)m * p.N + n] = __float2half_rn(a);
                         }
                     }
                 } else {
@@ -283,7 +325,7 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                     const int slot = unit_owner(tile * G, p.U, P);
                     float* sl = p.slots + (size_t)slot * kSlotFloats + (size_t)col0 * kTileN + r;
 #pragma unroll
-                    for (int j = 0; j < CPT; j++) atomicAdd(sl + j * kTileN, acc[j]);
+                    for (int j = 0; j < CPT; j++) atomicAdd(sl + j * kTileN, (j & 1) ? acc[j / 2].y : acc[j / 2].x);
                     __threadfence();
                     named_bar_sync(1, 256);
                     if (e == 0) {
@@ -382,12 +424,23 @@ static int launch(const int8_t* xq, const GemmParams& p_in, cudaStream_t stream)
     return (int)cudaGetLastError();
 }
 
+// experiment knob: FLEXQ_MTILE_CAP=128 keeps prefill on the 128-token tile
+static int mtile_cap() {
+    static int cap = 0;
+    if (cap == 0) {
+        const char* e = getenv("FLEXQ_MTILE_CAP");
+        cap = e ? atoi(e) : 256;
+    }
+    return cap;
+}
+
 template <bool DUMP>
 static int dispatch(const int8_t* xq, const GemmParams& p, cudaStream_t stream) {
     if (p.M <= 16) return launch<16, DUMP>(xq, p, stream);
     if (p.M <= 32) return launch<32, DUMP>(xq, p, stream);
     if (p.M <= 64) return launch<64, DUMP>(xq, p, stream);
-    return launch<128, DUMP>(xq, p, stream);
+    if (p.M <= 128 || mtile_cap() < 256) return launch<128, DUMP>(xq, p, stream);
+    return launch<256, DUMP>(xq, p, stream);
 }
 
 int gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const __half* w_scale, __half* D, int M, int N, int K,
