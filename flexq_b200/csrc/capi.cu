@@ -13,6 +13,7 @@ int planes_to_i8(const uint32_t*, int8_t*, int, int, int, cudaStream_t);
 int xscale_ref_to_sx(const __half*, float*, int, int, cudaStream_t);
 int gemm_w6ax(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, size_t, cudaStream_t);
 int gemm_w6ax_groupsums(const int8_t*, const uint8_t*, int32_t*, int, int, int, cudaStream_t);
+int gemm_w6ax_trace(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, long long*, int, cudaStream_t);
 }  // namespace flexq
 
 using namespace flexq;
@@ -88,6 +89,11 @@ int flexq_w6_to_i8(const uint8_t* w6, int8_t* out, int N, int K, void* stream) {
 int flexq_gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale, void* d, int M, int N, int K,
                     void* ws, size_t ws_bytes, void* stream) {
     return gemm_w6ax(xq, sx, w6, (const __half*)w_scale, (__half*)d, M, N, K, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int flexq_debug_gemm_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale, void* d, int M, int N, int K,
+                           void* ws, long long* trace, int trace_units, void* stream) {
+    return gemm_w6ax_trace(xq, sx, w6, (const __half*)w_scale, (__half*)d, M, N, K, ws, trace, trace_units, (cudaStream_t)stream);
 }
 
 int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K, void* stream) {

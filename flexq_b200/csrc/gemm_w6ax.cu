@@ -37,27 +37,42 @@ struct GemmParams {
     int M, N, K, G, ldsx;
     int m_tiles;             // tile index = nt * m_tiles + mt
     int U;                   // total units
+    long long* trace;        // TRACE builds: [unit][16] clock64 stamps of CTA 0
+    int trace_units;
 };
+
+#define FQ_TRACE(unit, ev)                                                                   \
+    do {                                                                                     \
+        if constexpr (TRACE) {                                                               \
+            if (blockIdx.x == 0 && (unit) < p.trace_units) p.trace[(unit) * 16 + (ev)] = clock64(); \
+        }                                                                                    \
+    } while (0)
 
 template <int M_TILE>
 struct Cfg {
+    static constexpr int SMEM_BUDGET = 224 * 1024;                 // of the 227 KB a CTA may use
+    static constexpr int NACC = (512 / M_TILE) < 8 ? (512 / M_TILE) : 8;   // TMEM accumulator buffers
     static constexpr int NA = 3;                                   // expanded-weight stages (16 KB)
-    static constexpr int NX = (M_TILE >= 256) ? 3 : 4;             // activation stages
-    static constexpr int NW = (M_TILE >= 256) ? 4 : (M_TILE >= 128 ? 6 : 10);   // packed-weight stages (12 KB)
+    static constexpr int NX = (M_TILE >= 256) ? 3 : (M_TILE >= 128 ? 4 : 6);   // activation stages
     static constexpr int NS = 8;                                   // scale stages (sx row + sw row)
     static constexpr int S_BYTES = M_TILE * 4 + kTileN * 2;        // f32 sx[M_TILE] | f16 sw[128]
     static constexpr int X_BYTES = M_TILE * 128;
     static constexpr int A_BYTES = kTileN * 128;
+    static constexpr int NW_FIT = (SMEM_BUDGET - 2048 - NA * A_BYTES - NX * X_BYTES - NS * S_BYTES) / kTileBytes;
+    static constexpr int NW = NW_FIT > 12 ? 12 : NW_FIT;           // packed-weight stages (12 KB each)
     static constexpr int OFF_A = 0;
     static constexpr int OFF_X = OFF_A + NA * A_BYTES;
     static constexpr int OFF_W = OFF_X + NX * X_BYTES;
     static constexpr int OFF_S = OFF_W + NW * kTileBytes;
     static constexpr int OFF_BAR = OFF_S + NS * S_BYTES;
-    static constexpr int NBAR = 2 * (NA + NX + NW + NS) + 4;
+    static constexpr int NDONE = 16;                               // "MMAs of unit u retired" ring (> NACC, NX, NA)
+    static constexpr int NBAR = 2 * (NW + NS) + NA + NX + NACC + NDONE;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_MISC + 16 + 1024;        // + alignment slack
-    static constexpr int TMEM_COLS = (2 * M_TILE < 32) ? 32 : 2 * M_TILE;
+    static constexpr int TMEM_COLS = (NACC * M_TILE < 32) ? 32 : NACC * M_TILE;
     static constexpr int CPT = M_TILE / 2;                         // columns per epilogue thread
+    static_assert(NW >= 4, "too few weight stages");
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
 };
 
 // owner(u) = the CTA whose unit range [floor(c*U/P), floor((c+1)*U/P)) contains u
@@ -65,7 +80,7 @@ __device__ __forceinline__ int unit_owner(int u, int U, int P) {
     return (int)((((long long)u + 1) * P - 1) / U);
 }
 
-template <int M_TILE, bool DUMP>
+template <int M_TILE, bool DUMP, bool TRACE = false>
 __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
     using C = Cfg<M_TILE>;
     extern __shared__ uint8_t smem_raw[];
@@ -81,24 +96,26 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
 
     // barrier addresses
     const uint32_t bar0 = smem_base + C::OFF_BAR;
-    auto bar_a_full = [&](int s) { return bar0 + 8u * s; };
-    auto bar_a_empty = [&](int s) { return bar0 + 8u * (C::NA + s); };
-    auto bar_x_full = [&](int s) { return bar0 + 8u * (2 * C::NA + s); };
-    auto bar_x_empty = [&](int s) { return bar0 + 8u * (2 * C::NA + C::NX + s); };
-    auto bar_w_full = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NX + s); };
-    auto bar_w_empty = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NX + C::NW + s); };
-    auto bar_s_full = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NX + 2 * C::NW + s); };
-    auto bar_s_empty = [&](int s) { return bar0 + 8u * (2 * C::NA + 2 * C::NX + 2 * C::NW + C::NS + s); };
-    auto bar_acc_full = [&](int b) { return bar0 + 8u * (2 * (C::NA + C::NX + C::NW + C::NS) + b); };
-    auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * (C::NA + C::NX + C::NW + C::NS) + 2 + b); };
+    // full/empty rings.  One tcgen05.commit per unit arrives on bar_done(unit % NDONE); it frees the
+    // activation stage and the expanded-weight stage of that unit and publishes its accumulator.
+    auto bar_w_full = [&](int s) { return bar0 + 8u * s; };
+    auto bar_w_empty = [&](int s) { return bar0 + 8u * (C::NW + s); };
+    auto bar_s_full = [&](int s) { return bar0 + 8u * (2 * C::NW + s); };
+    auto bar_s_empty = [&](int s) { return bar0 + 8u * (2 * C::NW + C::NS + s); };
+    auto bar_a_full = [&](int s) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + s); };
+    auto bar_x_full = [&](int s) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NA + s); };
+    auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NA + C::NX + b); };
+    auto bar_done = [&](int u) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NA + C::NX + C::NACC + (u % C::NDONE)); };
+    auto done_parity = [&](int u) { return (uint32_t)((u / C::NDONE) & 1); };
     uint32_t* misc = reinterpret_cast<uint32_t*>(smem + C::OFF_MISC);   // [0] tmem base, [1] finisher flag
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::NA; s++) { mbar_init(bar_a_full(s), 128); mbar_init(bar_a_empty(s), 1); }
-        for (int s = 0; s < C::NX; s++) { mbar_init(bar_x_full(s), 1); mbar_init(bar_x_empty(s), 1); }
+        for (int s = 0; s < C::NA; s++) mbar_init(bar_a_full(s), 128);
+        for (int s = 0; s < C::NX; s++) mbar_init(bar_x_full(s), 1);
         for (int s = 0; s < C::NW; s++) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 128); }
         for (int s = 0; s < C::NS; s++) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), 256); }
-        for (int b = 0; b < 2; b++) { mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), 256); }
+        for (int b = 0; b < C::NACC; b++) mbar_init(bar_acc_empty(b), 256);
+        for (int u = 0; u < C::NDONE; u++) mbar_init(bar_done(u), 1);
         fence_barrier_init();
         prefetch_tensormap(&tmap_x);
     }
@@ -112,39 +129,67 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
     // epilogue warpgroups 200 each (fp32 tile accumulators live in registers).
     // (setmaxnreg sits inside each role branch so that ptxas allocates per role.)
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        reg_dealloc<40>();
+        // ===================== TMA producer: packed weight tiles =====================
+        // (three independent producer threads -- weights, activations, scales -- so that the HBM
+        //  weight stream runs NW stages ahead instead of being gated by the activation ring)
+        reg_dealloc<32>();
         if (lane == 0) {
-            int iw = 0, ix = 0, is = 0;
+            int iw = 0;
+            for (int u = u_begin; u < u_end;) {
+                const int tile = u / G, g0 = u - tile * G;
+                const int g1 = min(G, g0 + (u_end - u));
+                const int nt = tile / p.m_tiles;
+                const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
+                for (int g = g0; g < g1; g++, iw++) {
+                    const int s = iw % C::NW;
+                    mbar_wait(bar_w_empty(s), ((iw / C::NW) & 1) ^ 1);
+                    FQ_TRACE(iw, 0);
+                    mbar_expect_tx(bar_w_full(s), kTileBytes);
+                    bulk_g2s(smem_base + C::OFF_W + s * kTileBytes, wsrc + (size_t)g * kTileBytes, kTileBytes, bar_w_full(s));
+                }
+                u += g1 - g0;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ===================== TMA producer: activation tiles =====================
+        reg_dealloc<32>();
+        if (lane == 0) {
+            int ix = 0;
+            for (int u = u_begin; u < u_end;) {
+                const int tile = u / G, g0 = u - tile * G;
+                const int g1 = min(G, g0 + (u_end - u));
+                const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+                for (int g = g0; g < g1; g++, ix++) {   // M_TILE rows x 128 B, swizzle-128B, rows >= M zero-filled
+                    const int s = ix % C::NX;
+                    if (ix >= C::NX) mbar_wait(bar_done(ix - C::NX), done_parity(ix - C::NX));
+                    FQ_TRACE(ix, 9);
+                    mbar_expect_tx(bar_x_full(s), C::X_BYTES);
+                    tma_load_2d(smem_base + C::OFF_X + s * C::X_BYTES, &tmap_x, g * kGroup, mt * M_TILE, bar_x_full(s));
+                }
+                u += g1 - g0;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 3) {
+        // ===================== TMA producer: scales =====================
+        reg_dealloc<32>();
+        if (lane == 0 && !DUMP) {
+            int is = 0;
             for (int u = u_begin; u < u_end;) {
                 const int tile = u / G, g0 = u - tile * G;
                 const int g1 = min(G, g0 + (u_end - u));
                 const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
                 const int m0 = mt * M_TILE;
-                const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
-                for (int g = g0; g < g1; g++) {
-                    {   // packed weight tile (one contiguous 12 KB block)
-                        const int s = iw % C::NW; const uint32_t ph = (iw / C::NW) & 1; iw++;
-                        mbar_wait(bar_w_empty(s), ph ^ 1);
-                        mbar_expect_tx(bar_w_full(s), kTileBytes);
-                        bulk_g2s(smem_base + C::OFF_W + s * kTileBytes, wsrc + (size_t)g * kTileBytes, kTileBytes, bar_w_full(s));
-                    }
-                    {   // activation tile: M_TILE rows x 128 B, swizzle-128B, rows >= M zero-filled
-                        const int s = ix % C::NX; const uint32_t ph = (ix / C::NX) & 1; ix++;
-                        mbar_wait(bar_x_empty(s), ph ^ 1);
-                        mbar_expect_tx(bar_x_full(s), C::X_BYTES);
-                        tma_load_2d(smem_base + C::OFF_X + s * C::X_BYTES, &tmap_x, g * kGroup, m0, bar_x_full(s));
-                    }
-                    if (!DUMP) {   // scales of this group: sx[g][m0..] (f32) and w_scale[g][n0..] (f16)
-                        const int s = is % C::NS; const uint32_t ph = (is / C::NS) & 1; is++;
-                        const int cols = min(M_TILE, p.ldsx - m0);
-                        const int rows = min(kTileN, p.N - nt * kTileN);
-                        const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
-                        mbar_wait(bar_s_empty(s), ph ^ 1);
-                        mbar_expect_tx(bar_s_full(s), cols * 4 + rows * 2);
-                        bulk_g2s(dst, p.sx + (size_t)g * p.ldsx + m0, cols * 4, bar_s_full(s));
-                        bulk_g2s(dst + M_TILE * 4, p.w_scale + (size_t)g * p.N + nt * kTileN, rows * 2, bar_s_full(s));
-                    }
+                const int cols = min(M_TILE, p.ldsx - m0);
+                const int rows = min(kTileN, p.N - nt * kTileN);
+                for (int g = g0; g < g1; g++, is++) {   // sx[g][m0..] (f32) and w_scale[g][n0..] (f16)
+                    const int s = is % C::NS;
+                    const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
+                    mbar_wait(bar_s_empty(s), ((is / C::NS) & 1) ^ 1);
+                    mbar_expect_tx(bar_s_full(s), cols * 4 + rows * 2);
+                    bulk_g2s(dst, p.sx + (size_t)g * p.ldsx + m0, cols * 4, bar_s_full(s));
+                    bulk_g2s(dst + M_TILE * 4, p.w_scale + (size_t)g * p.N + nt * kTileN, rows * 2, bar_s_full(s));
                 }
                 u += g1 - g0;
             }
@@ -152,39 +197,43 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        reg_dealloc<40>();
-        if (lane == 0) {
+        reg_dealloc<32>();
+        {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
             const int n_units = u_end - u_begin;
             for (int i = 0; i < n_units; i++) {
-                const int buf = i & 1;
+                const int buf = i % C::NACC;
                 const int sa = i % C::NA, sx_ = i % C::NX;
-                mbar_wait(bar_acc_empty(buf), (i >> 1) & 1);      // armed (biased) by the epilogue warps
-                mbar_wait(bar_x_full(sx_), (i / C::NX) & 1);
-                mbar_wait(bar_a_full(sa), (i / C::NA) & 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_base + C::OFF_A + sa * C::A_BYTES;
-                const uint32_t b_addr = smem_base + C::OFF_X + sx_ * C::X_BYTES;
-                const uint32_t d_tmem = tmem_base + buf * M_TILE;
+                // (divergent per-lane waits were measured slower than one lane waiting in turn)
+                if (lane == 0) {
+                    mbar_wait(bar_acc_empty(buf), (i / C::NACC) & 1);   // armed (biased) by the epilogue
+                    mbar_wait(bar_x_full(sx_), (i / C::NX) & 1);
+                    mbar_wait(bar_a_full(sa), (i / C::NA) & 1);
+                }
+                if (lane == 0) {
+                    FQ_TRACE(i, 4);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + C::OFF_A + sa * C::A_BYTES;
+                    const uint32_t b_addr = smem_base + C::OFF_X + sx_ * C::X_BYTES;
+                    const uint32_t d_tmem = tmem_base + buf * M_TILE;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    umma_i8(d_tmem, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc, 1u);
-                umma_commit(bar_x_empty(sx_));
-                umma_commit(bar_a_empty(sa));
-                umma_commit(bar_acc_full(buf));
+                    for (int k = 0; k < 4; k++)
+                        umma_i8(d_tmem, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc, 1u);
+                    umma_commit(bar_done(i));
+                    FQ_TRACE(i, 5);
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
-    } else if (warp < 4) {
-        reg_dealloc<40>();                               // idle warps of warpgroup 0
     } else if (warp < 8) {
         // ===================== weight expanders =====================
-        reg_dealloc<72>();
+        reg_dealloc<64>();
         const int r = threadIdx.x - 128;                 // weight row within the tile
         const int n_units = u_end - u_begin;
         for (int i = 0; i < n_units; i++) {
             const int sw = i % C::NW, sa = i % C::NA;
             mbar_wait(bar_w_full(sw), (i / C::NW) & 1);
+            if (r == 0) FQ_TRACE(i, 1);
             const uint8_t* wp = smem + C::OFF_W + sw * kTileBytes;
             uint4 in[2][3];
 #pragma unroll
@@ -193,7 +242,8 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                 in[q][0] = src[0]; in[q][1] = src[1]; in[q][2] = src[2];
             }
             mbar_arrive(bar_w_empty(sw));                // packed tile fully in registers
-            mbar_wait(bar_a_empty(sa), ((i / C::NA) & 1) ^ 1);
+            if (i >= C::NA) mbar_wait(bar_done(i - C::NA), done_parity(i - C::NA));
+            if (r == 0) FQ_TRACE(i, 2);
             uint8_t* arow = smem + C::OFF_A + sa * C::A_BYTES + r * 128;
 #pragma unroll
             for (int q = 0; q < 2; q++) {
@@ -209,16 +259,17 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
             }
             fence_proxy_async_smem();
             mbar_arrive(bar_a_full(sa));
+            if (r == 0) FQ_TRACE(i, 3);
         }
     } else {
         // ===================== epilogue =====================
-        reg_alloc<200>();
+        reg_alloc<208>();
         // Accumulators are re-armed with the bit pattern of 1.5*2^23 before every group, so the
         // int32 sum 4*S read back from TMEM *is* the float (kMagicF + 4*S): one FMA with the
         // per-row weight scale removes the bias exactly (kMagicF*sw is exact in fp32 for an
         // fp16-valued sw) and a second FMA applies the per-token scale and accumulates.
         constexpr int CPT = C::CPT;
-        constexpr int CH = CPT < 32 ? CPT : 32;          // columns per tcgen05.ld
+        constexpr int CH = CPT >= 128 ? 16 : (CPT < 32 ? CPT : 32);   // columns per tcgen05.ld (register budget)
         constexpr uint32_t kMagicI = 0x4B400000u;
         constexpr float kMagicF = 12582912.f;
         const int e = threadIdx.x - 256;
@@ -227,9 +278,9 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
         const int r = quad * 32 + lane;
         const int col0 = half_id * CPT;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
-        // arm both accumulator buffers once
+        // arm every accumulator buffer once
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < C::NACC; b++) {
 #pragma unroll
             for (int c = 0; c < CPT; c += (CPT < 16 ? 8 : 16)) {
                 if constexpr (CPT < 16) tmem_st8_same(t_lane + b * M_TILE + c, kMagicI);
@@ -238,8 +289,8 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(bar_acc_empty(0));
-        mbar_arrive(bar_acc_empty(1));
+#pragma unroll
+        for (int b = 0; b < C::NACC; b++) mbar_arrive(bar_acc_empty(b));
 
         float2 acc[CPT / 2];
         int i = 0, is = 0;
@@ -253,7 +304,7 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < CPT / 2; j++) acc[j] = make_float2(0.f, 0.f);
             for (int g = g0; g < g1; g++, i++) {
-                const int buf = i & 1;
+                const int buf = i % C::NACC;
                 float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
                 const float* sxs = nullptr;
                 int ss = 0;
@@ -267,7 +318,8 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                     sw2 = make_float2(swv, swv);
                     bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
                 }
-                mbar_wait(bar_acc_full(buf), (i >> 1) & 1);
+                mbar_wait(bar_done(i), done_parity(i));
+                if (e == 0) FQ_TRACE(i, 6);
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < CPT; c += CH) {
@@ -287,6 +339,7 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                         tmem_wait_st();
                         tc_fence_before();
                         mbar_arrive(bar_acc_empty(buf));
+                        if (e == 0) FQ_TRACE(i, 7);
                     }
                     if constexpr (DUMP) {
                         if (n_ok) {
@@ -308,6 +361,7 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                     }
                 }
                 if (!DUMP) mbar_arrive(bar_s_empty(ss));
+                if (e == 0) FQ_TRACE(i, 8);
             }
             if constexpr (!DUMP) {
                 if (g0 == 0 && g1 == G) {
@@ -326,17 +380,16 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                     float* sl = p.slots + (size_t)slot * kSlotFloats + (size_t)col0 * kTileN + r;
 #pragma unroll
                     for (int j = 0; j < CPT; j++) atomicAdd(sl + j * kTileN, (j & 1) ? acc[j / 2].y : acc[j / 2].x);
-                    __threadfence();
-                    named_bar_sync(1, 256);
+                    named_bar_sync(1, 256);              // every thread's red.adds are issued ...
                     if (e == 0) {
+                        __threadfence();                 // ... and released (cumulatively) by one fence
                         const int old = atomicAdd(p.cnt + slot, g1 - g0);
+                        __threadfence();
                         misc[1] = (old + (g1 - g0) == G) ? 1u : 0u;
                     }
                     named_bar_sync(1, 256);
                     const bool last = misc[1] != 0;
-                    named_bar_sync(1, 256);              // everyone has read the flag before it is reused
                     if (last) {
-                        __threadfence();
 #pragma unroll
                         for (int j = 0; j < CPT; j++) {
                             const float vsum = __ldcg(sl + j * kTileN);
@@ -346,6 +399,7 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
                         }
                         if (e == 0) p.cnt[slot] = 0;
                     }
+                    named_bar_sync(1, 256);              // flag word is reused by the next partial segment
                 }
             }
             u += g1 - g0;
@@ -391,7 +445,7 @@ static int num_sms() {
     return n;
 }
 
-template <int M_TILE, bool DUMP>
+template <int M_TILE, bool DUMP, bool TRACE = false>
 static int launch(const int8_t* xq, const GemmParams& p_in, cudaStream_t stream) {
     using C = Cfg<M_TILE>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget exceeded");
@@ -417,10 +471,10 @@ static int launch(const int8_t* xq, const GemmParams& p_in, cudaStream_t stream)
 
     static bool attr_set = false;
     if (!attr_set) {
-        FLEXQ_CUDA_TRY(cudaFuncSetAttribute(w6ax_gemm_kernel<M_TILE, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        FLEXQ_CUDA_TRY(cudaFuncSetAttribute(w6ax_gemm_kernel<M_TILE, DUMP, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    w6ax_gemm_kernel<M_TILE, DUMP><<<P, 512, C::SMEM_BYTES, stream>>>(tmap, p);
+    w6ax_gemm_kernel<M_TILE, DUMP, TRACE><<<P, 512, C::SMEM_BYTES, stream>>>(tmap, p);
     return (int)cudaGetLastError();
 }
 
@@ -454,6 +508,19 @@ int gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const __half
     p.slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
     p.M = M; p.N = N; p.K = K; p.G = K / kGroup; p.ldsx = ceil4(M);
     return dispatch<false>(xq, p, stream);
+}
+
+// debug: same GEMM with clock64 stamps of CTA 0's pipeline events (tools/trace.py)
+int gemm_w6ax_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const __half* w_scale, __half* D, int M, int N, int K,
+                    void* workspace, long long* trace, int trace_units, cudaStream_t stream) {
+    GemmParams p{};
+    p.w6 = w6; p.w_scale = w_scale; p.sx = sx; p.D = D; p.S = nullptr;
+    p.cnt = reinterpret_cast<int*>(workspace);
+    p.slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
+    p.M = M; p.N = N; p.K = K; p.G = K / kGroup; p.ldsx = ceil4(M);
+    p.trace = trace; p.trace_units = trace_units;
+    if (M <= 16) return launch<16, false, true>(xq, p, stream);
+    return launch<256, false, true>(xq, p, stream);
 }
 
 int gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K, cudaStream_t stream) {

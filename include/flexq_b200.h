@@ -112,6 +112,12 @@ int flexq_gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const 
 int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K,
                               void* stream);
 
+/* Debug only: the GEMM with clock64 stamps of CTA 0's pipeline events, trace[unit][16]
+ * (M <= 16 runs the decode tile, otherwise the 256-token tile); used by tools/trace.py. */
+int flexq_debug_gemm_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale_half,
+                           void* d_half, int M, int N, int K, void* workspace, long long* trace,
+                           int trace_units, void* stream);
+
 /* Fused linear: fp16 activations in, fp16 out (activation quantise + GEMM on one stream).
  * replaces: FLEXQGEMMWrapper::gemm(half* A ...) flexq_gemm_wrapper.cu:99-122 and is what
  * QuantLinear.forward (algorithm/flexq_quantize/int_linear.py:56-72) maps to.                   */

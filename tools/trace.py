@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Pipeline timeline of CTA 0 of the W6Ax GEMM (debug build with clock64 stamps)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from flexq_b200 import capi  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--m", type=int, default=16)
+ap.add_argument("--n", type=int, default=8192)
+ap.add_argument("--k", type=int, default=8192)
+ap.add_argument("--units", type=int, default=40)
+a = ap.parse_args()
+lib = capi.load()
+dev = torch.device("cuda")
+w6, wsc = capi.quant_pack_w6((0.02 * torch.randn(a.n, a.k, device=dev)).half())
+x = torch.randn(a.m, a.k, device=dev).half()
+xq, sx = capi.quant_act(x, 6)
+out = torch.empty(a.m, a.n, dtype=torch.float16, device=dev)
+ws = capi.new_workspace()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for it in range(3):
+    tr = torch.zeros(a.units, 16, dtype=torch.int64, device=dev)
+    flush.zero_()
+    capi.check(lib.flexq_debug_gemm_trace(capi._ptr(xq), capi._ptr(sx), capi._ptr(w6), capi._ptr(wsc), capi._ptr(out), a.m, a.n, a.k,
+                                          capi._ptr(ws), capi._ptr(tr), a.units, capi._stream()), "trace")
+    torch.cuda.synchronize()
+t = tr.cpu().numpy()
+t0 = t[t > 0].min()
+names = ["Wissue", "Wfull", "Aempty", "Afull", "MMArdy", "MMAcmt", "ACCfull", "ACCfree", "EPIend", "Xissue"]
+print("unit " + " ".join(f"{n:>8}" for n in names))
+for i in range(a.units):
+    print(f"{i:4d} " + " ".join(f"{(t[i, e] - t0) if t[i, e] else -1:8d}" for e in range(10)))
+d = np.diff(t[2:, 5])
+print("MMA commit interval cycles: mean %.0f median %.0f" % (d.mean(), np.median(d)))
