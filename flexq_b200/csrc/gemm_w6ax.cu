@@ -1,5 +1,6 @@
 // W6A6 / W6A8 GEMM for sm_100a: TMA-streamed packed 6-bit weights -> in-SM expansion to int8
-// -> tcgen05.mma kind::i8 (accumulators in TMEM) -> per-128-k-group scale epilogue -> fp16.
+// -> tcgen05.mma kind::i8 (weights read from TMEM, activations from shared memory, accumulators
+// in TMEM) -> per-128-k-group scale epilogue -> fp16.
 //
 // Replaces the reference's bit-serial BMMA kernel FQBMMAKernel::mainLoop
 // (/root/reference/engine/src/bgemm/flexq_bmma_kernel.h:119-447) and its launcher
@@ -9,16 +10,20 @@
 //
 // Orientation: the weight tile is the UMMA "A" operand (128 weight rows = UMMA M = TMEM lanes)
 // and the activations are the "B" operand (M_TILE tokens = UMMA N = TMEM columns), so decode
-// (1..16 tokens) and prefill (256-token tiles) run the same kernel with a different M_TILE.
+// (1..16 tokens) and prefill (192-token tiles) run the same kernel with different tile constants.
+// The expanded weights never touch shared memory: each expander thread owns one weight row,
+// turns its 96 packed bytes into 128 int8 in registers and writes them to TMEM with one
+// tcgen05.st, where the MMA reads them as its A operand.
 //
 // Work decomposition ("stream-K"): a unit is (n-tile, m-tile, k-group); the U units are split
 // evenly over P persistent CTAs (one per SM).  A CTA walks its units as segments of consecutive
-// groups of one tile.  A segment covering all groups of its tile stores fp16 directly; partial
-// segments are summed in an fp32 slot (red.global.add) and the CTA that completes the tile
-// converts, stores and re-zeroes the slot.
+// groups of one tile, GP groups per pipeline step.  A segment covering all groups of its tile
+// stores fp16 directly; partial segments are summed in an fp32 slot (red.global.add) and the CTA
+// that completes the tile converts, stores and re-zeroes the slot.
 //
-// Warp roles (512 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 4-7 = weight expanders (6 bit -> int8, swizzled UMMA layout), warps 8-15 = epilogue.
+// Warp roles (512 threads): warp 0 = TMA producer (weights), warps 1,2 = MMA issuers (alternate
+// steps; warp 1 also owns the TMEM allocation), warp 3 = TMA producer (activations + scales),
+// warps 4-7 = weight expanders, warps 8-15 = epilogue.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -28,16 +33,14 @@ namespace flexq {
 
 struct GemmParams {
     const uint8_t* w6;
-    const __half* w_scale;   // [G][N]
-    const float* sx;         // [G][ldsx]
     __half* D;               // [M][N]
     int32_t* S;              // [M][N][G] (DUMP only)
     float* slots;            // [kMaxCtas][M_TILE][128] fp32 partial tiles
     int* cnt;                // [kMaxCtas] group counters
-    int M, N, K, G, ldsx;
+    int M, N, K, G;
     int m_tiles;             // tile index = nt * m_tiles + mt
     int U;                   // total units
-    long long* trace;        // TRACE builds: [unit][16] clock64 stamps of CTA 0
+    long long* trace;        // TRACE builds: [step][16] clock64 stamps of CTA 0
     int trace_units;
 };
 
@@ -48,31 +51,39 @@ struct GemmParams {
         }                                                                                    \
     } while (0)
 
-template <int M_TILE>
+template <int M_TILE, int GP>
 struct Cfg {
-    static constexpr int SMEM_BUDGET = 224 * 1024;                 // of the 227 KB a CTA may use
-    static constexpr int NACC = (512 / M_TILE) < 8 ? (512 / M_TILE) : 8;   // TMEM accumulator buffers
-    static constexpr int NA = 3;                                   // expanded-weight stages (16 KB)
-    static constexpr int NX = (M_TILE >= 256) ? 3 : (M_TILE >= 128 ? 4 : 6);   // activation stages
-    static constexpr int NS = 8;                                   // scale stages (sx row + sw row)
-    static constexpr int S_BYTES = M_TILE * 4 + kTileN * 2;        // f32 sx[M_TILE] | f16 sw[128]
-    static constexpr int X_BYTES = M_TILE * 128;
-    static constexpr int A_BYTES = kTileN * 128;
-    static constexpr int NW_FIT = (SMEM_BUDGET - 2048 - NA * A_BYTES - NX * X_BYTES - NS * S_BYTES) / kTileBytes;
-    static constexpr int NW = NW_FIT > 12 ? 12 : NW_FIT;           // packed-weight stages (12 KB each)
-    static constexpr int OFF_A = 0;
-    static constexpr int OFF_X = OFF_A + NA * A_BYTES;
+    static constexpr int SMEM_BUDGET = 222 * 1024;                 // of the 227 KB a CTA may use
+    // ---- TMEM columns: NAB accumulator step-buffers (GP groups x M_TILE) + NAT weight stages (GP x 32)
+    static constexpr int ACC_COLS = GP * M_TILE;
+    static constexpr int A_COLS = GP * 32;
+    static constexpr int NAB = (M_TILE * GP <= 64) ? 4 : ((M_TILE == 128) ? 3 : 2);
+    static constexpr int NAT_FIT = (512 - NAB * ACC_COLS) / A_COLS;
+    static constexpr int NAT = NAT_FIT > 4 ? 4 : NAT_FIT;
+    static constexpr int A_COL0 = NAB * ACC_COLS;
+    static_assert(NAT >= 2 && NAB * ACC_COLS + NAT * A_COLS <= 512, "TMEM budget");
+    // ---- shared memory rings
+    static constexpr int NX = (M_TILE >= 128) ? 4 : 3;             // activation stages
+    static constexpr int NS = (M_TILE >= 128) ? 4 : 3;             // scale stages
+    static constexpr int X_BYTES = GP * M_TILE * 128;              // [GP][M_TILE][128 B], swizzle-128B
+    static constexpr int SX_BYTES = GP * M_TILE * 4;               // f32 [GP][M_TILE]
+    static constexpr int SW_BYTES = GP * kTileN * 2;               // f16 [GP][128]
+    static constexpr int S_BYTES = SX_BYTES + SW_BYTES;
+    static constexpr int W_BYTES = GP * kTileBytes;                // GP consecutive packed tiles
+    static constexpr int NW_FIT = (SMEM_BUDGET - NX * X_BYTES - NS * S_BYTES) / W_BYTES;
+    static constexpr int NW = NW_FIT > 10 ? 10 : NW_FIT;
+    static_assert(NW >= 3, "too few weight stages");
+    static constexpr int OFF_X = 0;
     static constexpr int OFF_W = OFF_X + NX * X_BYTES;
-    static constexpr int OFF_S = OFF_W + NW * kTileBytes;
+    static constexpr int OFF_S = OFF_W + NW * W_BYTES;
     static constexpr int OFF_BAR = OFF_S + NS * S_BYTES;
-    static constexpr int NDONE = 16;                               // "MMAs of unit u retired" ring (> NACC, NX, NA)
-    static constexpr int NBAR = 2 * (NW + NS) + NA + NX + NACC + NDONE;
+    static constexpr int NDONE = 16;                               // "MMAs of step i retired" ring (> NAB, NAT, NX)
+    static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_MISC + 16 + 1024;        // + alignment slack
-    static constexpr int TMEM_COLS = (NACC * M_TILE < 32) ? 32 : NACC * M_TILE;
     static constexpr int CPT = M_TILE / 2;                         // columns per epilogue thread
-    static_assert(NW >= 4, "too few weight stages");
-    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+    static constexpr int CH = CPT < 32 ? CPT : 32;                 // columns per tcgen05.ld
+    static_assert(CPT % CH == 0 && (CH == 8 || CH == 16 || CH == 32), "epilogue chunking");
 };
 
 // owner(u) = the CTA whose unit range [floor(c*U/P), floor((c+1)*U/P)) contains u
@@ -80,9 +91,11 @@ __device__ __forceinline__ int unit_owner(int u, int U, int P) {
     return (int)((((long long)u + 1) * P - 1) / U);
 }
 
-template <int M_TILE, bool DUMP, bool TRACE = false>
-__global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
-    using C = Cfg<M_TILE>;
+template <int M_TILE, int GP, bool DUMP, bool TRACE>
+__global__ void __launch_bounds__(512, 1)
+w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_sx,
+                 const __grid_constant__ CUtensorMap tmap_sw, const GemmParams p) {
+    using C = Cfg<M_TILE, GP>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -94,182 +107,179 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
     const int u_end = (int)(((long long)(blockIdx.x + 1) * p.U) / P);
     const int G = p.G;
 
-    // barrier addresses
+    // full/empty rings.  One tcgen05.commit per step arrives on bar_done(step % NDONE); it frees the
+    // activation stage and the TMEM weight stage of that step and publishes its accumulators.
     const uint32_t bar0 = smem_base + C::OFF_BAR;
-    // full/empty rings.  One tcgen05.commit per unit arrives on bar_done(unit % NDONE); it frees the
-    // activation stage and the expanded-weight stage of that unit and publishes its accumulator.
     auto bar_w_full = [&](int s) { return bar0 + 8u * s; };
     auto bar_w_empty = [&](int s) { return bar0 + 8u * (C::NW + s); };
     auto bar_s_full = [&](int s) { return bar0 + 8u * (2 * C::NW + s); };
     auto bar_s_empty = [&](int s) { return bar0 + 8u * (2 * C::NW + C::NS + s); };
     auto bar_a_full = [&](int s) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + s); };
-    auto bar_x_full = [&](int s) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NA + s); };
-    auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NA + C::NX + b); };
-    auto bar_done = [&](int u) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NA + C::NX + C::NACC + (u % C::NDONE)); };
-    auto done_parity = [&](int u) { return (uint32_t)((u / C::NDONE) & 1); };
+    auto bar_x_full = [&](int s) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NAT + s); };
+    auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NAT + C::NX + b); };
+    auto bar_done = [&](int i) { return bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NAT + C::NX + C::NAB + (i % C::NDONE)); };
+    auto done_parity = [&](int i) { return (uint32_t)((i / C::NDONE) & 1); };
     uint32_t* misc = reinterpret_cast<uint32_t*>(smem + C::OFF_MISC);   // [0] tmem base, [1] finisher flag
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::NA; s++) mbar_init(bar_a_full(s), 128);
+        for (int s = 0; s < C::NAT; s++) mbar_init(bar_a_full(s), 128);
         for (int s = 0; s < C::NX; s++) mbar_init(bar_x_full(s), 1);
         for (int s = 0; s < C::NW; s++) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 128); }
         for (int s = 0; s < C::NS; s++) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), 256); }
-        for (int b = 0; b < C::NACC; b++) mbar_init(bar_acc_empty(b), 256);
-        for (int u = 0; u < C::NDONE; u++) mbar_init(bar_done(u), 1);
+        for (int b = 0; b < C::NAB; b++) mbar_init(bar_acc_empty(b), 256);
+        for (int i = 0; i < C::NDONE; i++) mbar_init(bar_done(i), 1);
         fence_barrier_init();
         prefetch_tensormap(&tmap_x);
+        prefetch_tensormap(&tmap_sx);
+        prefetch_tensormap(&tmap_sw);
     }
-    if (warp == 1) tmem_alloc<C::TMEM_COLS>(smem_u32(&misc[0]));
+    if (warp == 1) tmem_alloc<512>(smem_u32(&misc[0]));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = misc[0];
 
-    // Register budget (64K regs, 512 threads): producer/MMA warpgroup 40, expanders 72, the two
-    // epilogue warpgroups 200 each (fp32 tile accumulators live in registers).
-    // (setmaxnreg sits inside each role branch so that ptxas allocates per role.)
+    // Every role walks the same sequence of steps:
+    //   for each segment (tile, [g0,g1)) of this CTA's unit range, for g = g0; g < g1; g += GP
+    // Register budget (64K regs): producer/MMA warpgroup 32, expanders 72, epilogue 200
+    // (setmaxnreg sits inside each role branch so that ptxas allocates per role).
     if (warp == 0) {
         // ===================== TMA producer: packed weight tiles =====================
-        // (three independent producer threads -- weights, activations, scales -- so that the HBM
-        //  weight stream runs NW stages ahead instead of being gated by the activation ring)
         reg_dealloc<32>();
         if (lane == 0) {
-            int iw = 0;
+            int it = 0;
             for (int u = u_begin; u < u_end;) {
                 const int tile = u / G, g0 = u - tile * G;
                 const int g1 = min(G, g0 + (u_end - u));
                 const int nt = tile / p.m_tiles;
                 const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
-                for (int g = g0; g < g1; g++, iw++) {
-                    const int s = iw % C::NW;
-                    mbar_wait(bar_w_empty(s), ((iw / C::NW) & 1) ^ 1);
-                    FQ_TRACE(iw, 0);
-                    mbar_expect_tx(bar_w_full(s), kTileBytes);
-                    bulk_g2s(smem_base + C::OFF_W + s * kTileBytes, wsrc + (size_t)g * kTileBytes, kTileBytes, bar_w_full(s));
-                }
-                u += g1 - g0;
-            }
-        }
-        __syncwarp();
-    } else if (warp == 2) {
-        // ===================== TMA producer: activation tiles =====================
-        reg_dealloc<32>();
-        if (lane == 0) {
-            int ix = 0;
-            for (int u = u_begin; u < u_end;) {
-                const int tile = u / G, g0 = u - tile * G;
-                const int g1 = min(G, g0 + (u_end - u));
-                const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
-                for (int g = g0; g < g1; g++, ix++) {   // M_TILE rows x 128 B, swizzle-128B, rows >= M zero-filled
-                    const int s = ix % C::NX;
-                    if (ix >= C::NX) mbar_wait(bar_done(ix - C::NX), done_parity(ix - C::NX));
-                    FQ_TRACE(ix, 9);
-                    mbar_expect_tx(bar_x_full(s), C::X_BYTES);
-                    tma_load_2d(smem_base + C::OFF_X + s * C::X_BYTES, &tmap_x, g * kGroup, mt * M_TILE, bar_x_full(s));
+                for (int g = g0; g < g1; g += GP, it++) {
+                    const int ng = min(GP, g1 - g);
+                    const int s = it % C::NW;
+                    mbar_wait(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
+                    FQ_TRACE(it, 0);
+                    mbar_expect_tx(bar_w_full(s), ng * kTileBytes);
+                    bulk_g2s(smem_base + C::OFF_W + s * C::W_BYTES, wsrc + (size_t)g * kTileBytes, ng * kTileBytes, bar_w_full(s));
                 }
                 u += g1 - g0;
             }
         }
         __syncwarp();
     } else if (warp == 3) {
-        // ===================== TMA producer: scales =====================
+        // ===================== TMA producer: activation tiles + scale blocks =====================
         reg_dealloc<32>();
-        if (lane == 0 && !DUMP) {
-            int is = 0;
+        if (lane == 0) {
+            int it = 0;
             for (int u = u_begin; u < u_end;) {
                 const int tile = u / G, g0 = u - tile * G;
                 const int g1 = min(G, g0 + (u_end - u));
                 const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
-                const int m0 = mt * M_TILE;
-                const int cols = min(M_TILE, p.ldsx - m0);
-                const int rows = min(kTileN, p.N - nt * kTileN);
-                for (int g = g0; g < g1; g++, is++) {   // sx[g][m0..] (f32) and w_scale[g][n0..] (f16)
-                    const int s = is % C::NS;
-                    const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
-                    mbar_wait(bar_s_empty(s), ((is / C::NS) & 1) ^ 1);
-                    mbar_expect_tx(bar_s_full(s), cols * 4 + rows * 2);
-                    bulk_g2s(dst, p.sx + (size_t)g * p.ldsx + m0, cols * 4, bar_s_full(s));
-                    bulk_g2s(dst + M_TILE * 4, p.w_scale + (size_t)g * p.N + nt * kTileN, rows * 2, bar_s_full(s));
+                for (int g = g0; g < g1; g += GP, it++) {
+                    {   // [ng][M_TILE][128 B] swizzle-128B tiles, one TMA per k-group; rows >= M are zero-filled
+                        const int ng = min(GP, g1 - g);
+                        const int s = it % C::NX;
+                        if (it >= C::NX) mbar_wait(bar_done(it - C::NX), done_parity(it - C::NX));
+                        FQ_TRACE(it, 9);
+                        mbar_expect_tx(bar_x_full(s), ng * (M_TILE * 128));
+                        for (int j = 0; j < ng; j++)
+                            tma_load_2d(smem_base + C::OFF_X + s * C::X_BYTES + j * (M_TILE * 128), &tmap_x, (g + j) * kGroup, mt * M_TILE,
+                                        bar_x_full(s));
+                    }
+                    if (!DUMP) {   // sx[g..g+GP][m0..] (f32) and w_scale[g..g+GP][n0..] (f16)
+                        const int s = it % C::NS;
+                        const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
+                        mbar_wait(bar_s_empty(s), ((it / C::NS) & 1) ^ 1);
+                        mbar_expect_tx(bar_s_full(s), C::S_BYTES);
+                        tma_load_2d(dst, &tmap_sx, mt * M_TILE, g, bar_s_full(s));
+                        tma_load_2d(dst + C::SX_BYTES, &tmap_sw, nt * kTileN, g, bar_s_full(s));
+                    }
                 }
                 u += g1 - g0;
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 2) {
+        // ===================== MMA issuers (steps alternate between the two warps) =====================
         reg_dealloc<32>();
-        {
+        if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
-            const int n_units = u_end - u_begin;
-            for (int i = 0; i < n_units; i++) {
-                const int buf = i % C::NACC;
-                const int sa = i % C::NA, sx_ = i % C::NX;
-                // (divergent per-lane waits were measured slower than one lane waiting in turn)
-                if (lane == 0) {
-                    mbar_wait(bar_acc_empty(buf), (i / C::NACC) & 1);   // armed (biased) by the epilogue
-                    mbar_wait(bar_x_full(sx_), (i / C::NX) & 1);
-                    mbar_wait(bar_a_full(sa), (i / C::NA) & 1);
-                }
-                if (lane == 0) {
-                    FQ_TRACE(i, 4);
+            int it = 0;
+            for (int u = u_begin; u < u_end;) {
+                const int tile = u / G, g0 = u - tile * G;
+                const int g1 = min(G, g0 + (u_end - u));
+                for (int g = g0; g < g1; g += GP, it++) {
+                    if ((it & 1) != (warp - 1)) continue;
+                    const int ng = min(GP, g1 - g);
+                    const int ab = it % C::NAB, st = it % C::NAT, sx_ = it % C::NX;
+                    mbar_wait(bar_acc_empty(ab), (it / C::NAB) & 1);   // armed (biased) by the epilogue
+                    mbar_wait(bar_x_full(sx_), (it / C::NX) & 1);
+                    mbar_wait(bar_a_full(st), (it / C::NAT) & 1);
+                    FQ_TRACE(it, 4);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + C::OFF_A + sa * C::A_BYTES;
                     const uint32_t b_addr = smem_base + C::OFF_X + sx_ * C::X_BYTES;
-                    const uint32_t d_tmem = tmem_base + buf * M_TILE;
+                    const uint32_t d_tmem = tmem_base + ab * C::ACC_COLS;
+                    const uint32_t a_tmem = tmem_base + C::A_COL0 + st * C::A_COLS;
+                    for (int j = 0; j < ng; j++) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        umma_i8(d_tmem, umma_desc_sw128(a_addr + 32 * k), umma_desc_sw128(b_addr + 32 * k), idesc, 1u);
-                    umma_commit(bar_done(i));
-                    FQ_TRACE(i, 5);
+                        for (int k = 0; k < 4; k++)
+                            umma_i8_ts(d_tmem + j * M_TILE, a_tmem + j * 32 + 8 * k,
+                                       umma_desc_sw128(b_addr + j * (M_TILE * 128) + 32 * k), idesc, 1u);
+                    }
+                    umma_commit(bar_done(it));
+                    FQ_TRACE(it, 5);
                 }
+                u += g1 - g0;
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp < 8) {
-        // ===================== weight expanders =====================
-        reg_dealloc<64>();
-        const int r = threadIdx.x - 128;                 // weight row within the tile
-        const int n_units = u_end - u_begin;
-        for (int i = 0; i < n_units; i++) {
-            const int sw = i % C::NW, sa = i % C::NA;
-            mbar_wait(bar_w_full(sw), (i / C::NW) & 1);
-            if (r == 0) FQ_TRACE(i, 1);
-            const uint8_t* wp = smem + C::OFF_W + sw * kTileBytes;
-            uint4 in[2][3];
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const uint4* src = reinterpret_cast<const uint4*>(wp + 48 * (128 * q + r));
-                in[q][0] = src[0]; in[q][1] = src[1]; in[q][2] = src[2];
-            }
-            mbar_arrive(bar_w_empty(sw));                // packed tile fully in registers
-            if (i >= C::NA) mbar_wait(bar_done(i - C::NA), done_parity(i - C::NA));
-            if (r == 0) FQ_TRACE(i, 2);
-            uint8_t* arow = smem + C::OFF_A + sa * C::A_BYTES + r * 128;
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const uint32_t w[12] = {in[q][0].x, in[q][0].y, in[q][0].z, in[q][0].w, in[q][1].x, in[q][1].y,
-                                        in[q][1].z, in[q][1].w, in[q][2].x, in[q][2].y, in[q][2].z, in[q][2].w};
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    uint32_t o[4];
-                    w6_expand16(w[3 * s], w[3 * s + 1], w[3 * s + 2], o);
-                    const int chunk = (4 * q + s) ^ (r & 7);     // 128-byte swizzle
-                    *reinterpret_cast<uint4*>(arow + 16 * chunk) = make_uint4(o[0], o[1], o[2], o[3]);
+        // ===================== weight expanders: smem (packed) -> registers -> TMEM (int8) =====================
+        reg_dealloc<72>();
+        const int r = threadIdx.x - 128;                 // weight row within the tile == TMEM lane
+        const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0;
+        int it = 0;
+        for (int u = u_begin; u < u_end;) {
+            const int tile = u / G, g0 = u - tile * G;
+            const int g1 = min(G, g0 + (u_end - u));
+            for (int g = g0; g < g1; g += GP, it++) {
+                const int ng = min(GP, g1 - g);
+                const int sw = it % C::NW, st = it % C::NAT;
+                mbar_wait(bar_w_full(sw), (it / C::NW) & 1);
+                if (r == 0) FQ_TRACE(it, 1);
+                if (it >= C::NAT) {                      // MMAs that read this TMEM stage have retired
+                    mbar_wait(bar_done(it - C::NAT), done_parity(it - C::NAT));
+                    tc_fence_after();
                 }
+                if (r == 0) FQ_TRACE(it, 2);
+                const uint8_t* wp = smem + C::OFF_W + sw * C::W_BYTES;
+                for (int j = 0; j < ng; j++) {
+                    uint32_t out[32];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const uint4* src = reinterpret_cast<const uint4*>(wp + j * kTileBytes + 48 * (128 * q + r));
+                        const uint4 i0 = src[0], i1 = src[1], i2 = src[2];
+                        const uint32_t w[12] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
+#pragma unroll
+                        for (int s = 0; s < 4; s++) w6_expand16(w[3 * s], w[3 * s + 1], w[3 * s + 2], out + 16 * q + 4 * s);
+                    }
+                    tmem_st32(a_lane + st * C::A_COLS + j * 32, out);   // this row's 128 int8 (value 4*w)
+                }
+                mbar_arrive(bar_w_empty(sw));            // packed tiles consumed
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_a_full(st));
+                if (r == 0) FQ_TRACE(it, 3);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(bar_a_full(sa));
-            if (r == 0) FQ_TRACE(i, 3);
+            u += g1 - g0;
         }
     } else {
         // ===================== epilogue =====================
-        reg_alloc<208>();
         // Accumulators are re-armed with the bit pattern of 1.5*2^23 before every group, so the
         // int32 sum 4*S read back from TMEM *is* the float (kMagicF + 4*S): one FMA with the
         // per-row weight scale removes the bias exactly (kMagicF*sw is exact in fp32 for an
         // fp16-valued sw) and a second FMA applies the per-token scale and accumulates.
-        constexpr int CPT = C::CPT;
-        constexpr int CH = CPT >= 128 ? 16 : (CPT < 32 ? CPT : 32);   // columns per tcgen05.ld (register budget)
+        reg_alloc<200>();
+        constexpr int CPT = C::CPT, CH = C::CH;
         constexpr uint32_t kMagicI = 0x4B400000u;
         constexpr float kMagicF = 12582912.f;
         const int e = threadIdx.x - 256;
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
         // arm every accumulator buffer once
 #pragma unroll
-        for (int b = 0; b < C::NACC; b++) {
+        for (int b = 0; b < C::NAB * GP; b++) {
 #pragma unroll
             for (int c = 0; c < CPT; c += (CPT < 16 ? 8 : 16)) {
                 if constexpr (CPT < 16) tmem_st8_same(t_lane + b * M_TILE + c, kMagicI);
@@ -290,10 +300,10 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
         tmem_wait_st();
         tc_fence_before();
 #pragma unroll
-        for (int b = 0; b < C::NACC; b++) mbar_arrive(bar_acc_empty(b));
+        for (int b = 0; b < C::NAB; b++) mbar_arrive(bar_acc_empty(b));
 
         float2 acc[CPT / 2];
-        int i = 0, is = 0;
+        int it = 0;
         for (int u = u_begin; u < u_end;) {
             const int tile = u / G, g0 = u - tile * G;
             const int g1 = min(G, g0 + (u_end - u));
@@ -303,65 +313,62 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
             const bool n_ok = n < p.N;
 #pragma unroll
             for (int j = 0; j < CPT / 2; j++) acc[j] = make_float2(0.f, 0.f);
-            for (int g = g0; g < g1; g++, i++) {
-                const int buf = i % C::NACC;
-                float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
-                const float* sxs = nullptr;
-                int ss = 0;
-                if (!DUMP) {
-                    ss = is % C::NS;
-                    mbar_wait(bar_s_full(ss), (is / C::NS) & 1);
-                    is++;
-                    const uint8_t* st = smem + C::OFF_S + ss * C::S_BYTES;
-                    sxs = reinterpret_cast<const float*>(st) + col0;
-                    const float swv = n_ok ? 0.25f * __half2float(reinterpret_cast<const __half*>(st + M_TILE * 4)[r]) : 0.f;   // operands hold 4*w
-                    sw2 = make_float2(swv, swv);
-                    bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
-                }
-                mbar_wait(bar_done(i), done_parity(i));
-                if (e == 0) FQ_TRACE(i, 6);
+            for (int g = g0; g < g1; g += GP, it++) {
+                const int ng = min(GP, g1 - g);
+                const int ab = it % C::NAB, ss = it % C::NS;
+                const uint8_t* sblk = smem + C::OFF_S + ss * C::S_BYTES;
+                if (!DUMP) mbar_wait(bar_s_full(ss), (it / C::NS) & 1);
+                mbar_wait(bar_done(it), done_parity(it));
+                if (e == 0) FQ_TRACE(it, 6);
                 tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < CPT; c += CH) {
-                    uint32_t v[CH];
-                    const uint32_t ta = t_lane + buf * M_TILE + c;
-                    if constexpr (CH == 8) tmem_ld8(ta, v);
-                    else if constexpr (CH == 16) tmem_ld16(ta, v);
-                    else tmem_ld32(ta, v);
-                    tmem_wait_ld();
-                    // re-arm this chunk of the accumulator for its next group
-                    if constexpr (CH == 8) tmem_st8_same(ta, kMagicI);
-                    else {
-#pragma unroll
-                        for (int cc = 0; cc < CH; cc += 16) tmem_st16_same(ta + cc, kMagicI);
+                for (int j = 0; j < ng; j++) {
+                    float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
+                    const float* sxs = reinterpret_cast<const float*>(sblk) + j * M_TILE + col0;
+                    if (!DUMP) {
+                        const float swv = n_ok ? 0.25f * __half2float(reinterpret_cast<const __half*>(sblk + C::SX_BYTES)[j * kTileN + r]) : 0.f;   // operands hold 4*w
+                        sw2 = make_float2(swv, swv);
+                        bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
                     }
-                    if (c + CH >= CPT) {                 // accumulator fully read and re-armed: hand it back
-                        tmem_wait_st();
-                        tc_fence_before();
-                        mbar_arrive(bar_acc_empty(buf));
-                        if (e == 0) FQ_TRACE(i, 7);
-                    }
-                    if constexpr (DUMP) {
-                        if (n_ok) {
 #pragma unroll
-                            for (int j = 0; j < CH; j++) {
-                                const int m = mbase + c + j;
-                                if (m < p.M) p.S[((size_t)m * p.N + n) * G + g] = ((int32_t)(v[j] - kMagicI)) >> 2;
+                    for (int c = 0; c < CPT; c += CH) {
+                        uint32_t v[CH];
+                        const uint32_t ta = t_lane + ab * C::ACC_COLS + j * M_TILE + c;
+                        if constexpr (CH == 8) tmem_ld8(ta, v);
+                        else if constexpr (CH == 16) tmem_ld16(ta, v);
+                        else tmem_ld32(ta, v);
+                        tmem_wait_ld();
+                        // re-arm this chunk of the accumulator for its next use
+                        if constexpr (CH == 8) tmem_st8_same(ta, kMagicI);
+                        else {
+#pragma unroll
+                            for (int cc = 0; cc < CH; cc += 16) tmem_st16_same(ta + cc, kMagicI);
+                        }
+                        if constexpr (DUMP) {
+                            if (n_ok) {
+#pragma unroll
+                                for (int q = 0; q < CH; q++) {
+                                    const int m = mbase + c + q;
+                                    if (m < p.M) p.S[((size_t)m * p.N + n) * G + g + j] = ((int32_t)(v[q] - kMagicI)) >> 2;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < CH; q += 4) {
+                                const float4 s4 = *reinterpret_cast<const float4*>(sxs + c + q);
+                                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1])), sw2, bias2);
+                                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])), sw2, bias2);
+                                acc[(c + q) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c + q) / 2]);
+                                acc[(c + q) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c + q) / 2 + 1]);
                             }
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < CH; j += 4) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(sxs + c + j);
-                            const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), sw2, bias2);
-                            const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), sw2, bias2);
-                            acc[(c + j) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c + j) / 2]);
-                            acc[(c + j) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c + j) / 2 + 1]);
-                        }
                     }
                 }
+                // accumulators of this step fully read and re-armed: hand the buffer back
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_acc_empty(ab));
+                if (e == 0) FQ_TRACE(it, 7);
                 if (!DUMP) mbar_arrive(bar_s_empty(ss));
-                if (e == 0) FQ_TRACE(i, 8);
             }
             if constexpr (!DUMP) {
                 if (g0 == 0 && g1 == G) {
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(512, 1) w6ax_gemm_kernel(const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -445,24 +452,53 @@ static int num_sms() {
     return n;
 }
 
-template <int M_TILE, bool DUMP, bool TRACE = false>
-static int launch(const int8_t* xq, const GemmParams& p_in, cudaStream_t stream) {
-    using C = Cfg<M_TILE>;
+struct GemmArgs {
+    const int8_t* xq;
+    const float* sx;
+    const __half* w_scale;
+    GemmParams p;
+};
+
+template <int M_TILE, int GP, bool DUMP, bool TRACE = false>
+static int launch(const GemmArgs& a, cudaStream_t stream) {
+    using C = Cfg<M_TILE, GP>;
     static_assert(C::SMEM_BYTES <= 232448, "shared memory budget exceeded");
-    GemmParams p = p_in;
+    GemmParams p = a.p;
     PFN_tmapEncodeTiled enc = get_encode_fn();
     const int sms = num_sms();
     if (!enc || sms <= 0) return FLEXQ_ERR_NO_DEVICE;
+    const cuuint32_t ones[3] = {1u, 1u, 1u};
 
-    CUtensorMap tmap;
-    const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.K};
-    const cuuint32_t box[2] = {128u, (cuuint32_t)M_TILE};
-    const cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(xq), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return FLEXQ_ERR_TENSORMAP;
+    CUtensorMap tmap_x, tmap_sx, tmap_sw;
+    {   // activations [M][K] int8, box = 128 bytes of k x M_TILE tokens, 128-byte swizzle
+        const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+        const cuuint64_t strides[1] = {(cuuint64_t)p.K};
+        const cuuint32_t box[2] = {128u, (cuuint32_t)M_TILE};
+        if (enc(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(a.xq), dims, strides, box, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FLEXQ_ERR_TENSORMAP;
+    }
+    if (!DUMP) {
+        const int ldsx = ceil4(p.M);
+        const cuuint64_t dims_sx[2] = {(cuuint64_t)ldsx, (cuuint64_t)p.G};
+        const cuuint64_t str_sx[1] = {(cuuint64_t)ldsx * 4};
+        const cuuint32_t box_sx[2] = {(cuuint32_t)M_TILE, (cuuint32_t)GP};
+        if (enc(&tmap_sx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.sx), dims_sx, str_sx, box_sx, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FLEXQ_ERR_TENSORMAP;
+        const cuuint64_t dims_sw[2] = {(cuuint64_t)p.N, (cuuint64_t)p.G};
+        const cuuint64_t str_sw[1] = {(cuuint64_t)p.N * 2};
+        const cuuint32_t box_sw[2] = {(cuuint32_t)kTileN, (cuuint32_t)GP};
+        if (enc(&tmap_sw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a.w_scale), dims_sw, str_sw, box_sw, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FLEXQ_ERR_TENSORMAP;
+    } else {
+        tmap_sx = tmap_x;
+        tmap_sw = tmap_x;
+    }
 
     const int n_tiles = ceil_div(p.N, kTileN);
     p.m_tiles = ceil_div(p.M, M_TILE);
@@ -471,65 +507,62 @@ static int launch(const int8_t* xq, const GemmParams& p_in, cudaStream_t stream)
 
     static bool attr_set = false;
     if (!attr_set) {
-        FLEXQ_CUDA_TRY(cudaFuncSetAttribute(w6ax_gemm_kernel<M_TILE, DUMP, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        FLEXQ_CUDA_TRY(cudaFuncSetAttribute(w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    w6ax_gemm_kernel<M_TILE, DUMP, TRACE><<<P, 512, C::SMEM_BYTES, stream>>>(tmap, p);
+    w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE><<<P, 512, C::SMEM_BYTES, stream>>>(tmap_x, tmap_sx, tmap_sw, p);
     return (int)cudaGetLastError();
 }
 
-// experiment knob: FLEXQ_MTILE_CAP=128 keeps prefill on the 128-token tile
-static int mtile_cap() {
-    static int cap = 0;
-    if (cap == 0) {
-        const char* e = getenv("FLEXQ_MTILE_CAP");
-        cap = e ? atoi(e) : 256;
-    }
-    return cap;
+template <bool DUMP>
+static int dispatch(const GemmArgs& a, cudaStream_t stream) {
+    const int M = a.p.M;
+    if (M <= 16) return launch<16, 4, DUMP>(a, stream);
+    if (M <= 32) return launch<32, 4, DUMP>(a, stream);
+    if (M <= 64) return launch<64, 2, DUMP>(a, stream);
+    if (M <= 128) return launch<128, 1, DUMP>(a, stream);
+    return launch<192, 1, DUMP>(a, stream);
 }
 
-template <bool DUMP>
-static int dispatch(const int8_t* xq, const GemmParams& p, cudaStream_t stream) {
-    if (p.M <= 16) return launch<16, DUMP>(xq, p, stream);
-    if (p.M <= 32) return launch<32, DUMP>(xq, p, stream);
-    if (p.M <= 64) return launch<64, DUMP>(xq, p, stream);
-    if (p.M <= 128 || mtile_cap() < 256) return launch<128, DUMP>(xq, p, stream);
-    return launch<256, DUMP>(xq, p, stream);
+static int check_shape(int M, int N, int K) {
+    // N % 8: w_scale rows are fetched by TMA (16-byte row pitch), as the reference's 16-byte stores need
+    return (M <= 0 || N <= 0 || N % 8 || K < kGroup || K % kGroup) ? FLEXQ_ERR_BAD_SHAPE : 0;
+}
+
+static GemmArgs make_args(const int8_t* xq, const float* sx, const uint8_t* w6, const __half* w_scale, __half* D, int32_t* S,
+                          int M, int N, int K, void* workspace) {
+    GemmArgs a{};
+    a.xq = xq; a.sx = sx; a.w_scale = w_scale;
+    a.p.w6 = w6; a.p.D = D; a.p.S = S;
+    if (workspace) {
+        a.p.cnt = reinterpret_cast<int*>(workspace);
+        a.p.slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
+    }
+    a.p.M = M; a.p.N = N; a.p.K = K; a.p.G = K / kGroup;
+    return a;
 }
 
 int gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const __half* w_scale, __half* D, int M, int N, int K,
               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (!xq || !sx || !w6 || !w_scale || !D || !workspace) return FLEXQ_ERR_NULL;
-    if (M <= 0 || N <= 0 || K < kGroup || K % kGroup) return FLEXQ_ERR_BAD_SHAPE;
+    if (int e = check_shape(M, N, K)) return e;
     if (workspace_bytes < flexq_gemm_workspace_bytes() || ((uintptr_t)workspace & 15)) return FLEXQ_ERR_WORKSPACE;
-    GemmParams p{};
-    p.w6 = w6; p.w_scale = w_scale; p.sx = sx; p.D = D; p.S = nullptr;
-    p.cnt = reinterpret_cast<int*>(workspace);
-    p.slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
-    p.M = M; p.N = N; p.K = K; p.G = K / kGroup; p.ldsx = ceil4(M);
-    return dispatch<false>(xq, p, stream);
+    return dispatch<false>(make_args(xq, sx, w6, w_scale, D, nullptr, M, N, K, workspace), stream);
 }
 
 // debug: same GEMM with clock64 stamps of CTA 0's pipeline events (tools/trace.py)
 int gemm_w6ax_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const __half* w_scale, __half* D, int M, int N, int K,
                     void* workspace, long long* trace, int trace_units, cudaStream_t stream) {
-    GemmParams p{};
-    p.w6 = w6; p.w_scale = w_scale; p.sx = sx; p.D = D; p.S = nullptr;
-    p.cnt = reinterpret_cast<int*>(workspace);
-    p.slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
-    p.M = M; p.N = N; p.K = K; p.G = K / kGroup; p.ldsx = ceil4(M);
-    p.trace = trace; p.trace_units = trace_units;
-    if (M <= 16) return launch<16, false, true>(xq, p, stream);
-    return launch<256, false, true>(xq, p, stream);
+    GemmArgs a = make_args(xq, sx, w6, w_scale, D, nullptr, M, N, K, workspace);
+    a.p.trace = trace; a.p.trace_units = trace_units;
+    if (M <= 16) return launch<16, 4, false, true>(a, stream);
+    return launch<192, 1, false, true>(a, stream);
 }
 
 int gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K, cudaStream_t stream) {
     if (!xq || !w6 || !S) return FLEXQ_ERR_NULL;
-    if (M <= 0 || N <= 0 || K < kGroup || K % kGroup) return FLEXQ_ERR_BAD_SHAPE;
-    GemmParams p{};
-    p.w6 = w6; p.S = S;
-    p.M = M; p.N = N; p.K = K; p.G = K / kGroup; p.ldsx = ceil4(M);
-    return dispatch<true>(xq, p, stream);
+    if (int e = check_shape(M, N, K)) return e;
+    return dispatch<true>(make_args(xq, nullptr, w6, nullptr, nullptr, S, M, N, K, nullptr), stream);
 }
 
 }  // namespace flexq
