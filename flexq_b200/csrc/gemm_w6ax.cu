@@ -211,9 +211,16 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if ((it & 1) != (warp - 1)) continue;
                     const int ng = min(GP, g1 - g);
                     const int ab = it % C::NAB, st = it % C::NAT, sx_ = it % C::NX;
-                    mbar_wait(bar_acc_empty(ab), (it / C::NAB) & 1);   // armed (biased) by the epilogue
+                    // the barrier expected to complete last is waited on last (an already-complete wait
+                    // still costs ~200 cycles): accumulator hand-back when tensor-bound, weights when HBM-bound
                     mbar_wait(bar_x_full(sx_), (it / C::NX) & 1);
-                    mbar_wait(bar_a_full(st), (it / C::NAT) & 1);
+                    if (GP == 1) {
+                        mbar_wait(bar_a_full(st), (it / C::NAT) & 1);
+                        mbar_wait(bar_acc_empty(ab), (it / C::NAB) & 1);   // armed (biased) by the epilogue
+                    } else {
+                        mbar_wait(bar_acc_empty(ab), (it / C::NAB) & 1);
+                        mbar_wait(bar_a_full(st), (it / C::NAT) & 1);
+                    }
                     FQ_TRACE(it, 4);
                     tc_fence_after();
                     const uint32_t b_addr = smem_base + C::OFF_X + sx_ * C::X_BYTES;
