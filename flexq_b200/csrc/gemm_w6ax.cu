@@ -57,13 +57,13 @@ struct Cfg {
     // ---- TMEM columns: NAB accumulator step-buffers (GP groups x M_TILE) + NAT weight stages (GP x 32)
     static constexpr int ACC_COLS = GP * M_TILE;
     static constexpr int A_COLS = GP * 32;
-    static constexpr int NAB = (M_TILE * GP <= 64) ? 4 : ((M_TILE == 128) ? 3 : 2);
+    static constexpr int NAB = (M_TILE * GP <= 64) ? 4 : 2;
     static constexpr int NAT_FIT = (512 - NAB * ACC_COLS) / A_COLS;
     static constexpr int NAT = NAT_FIT > 4 ? 4 : NAT_FIT;
     static constexpr int A_COL0 = NAB * ACC_COLS;
     static_assert(NAT >= 2 && NAB * ACC_COLS + NAT * A_COLS <= 512, "TMEM budget");
     // ---- shared memory rings
-    static constexpr int NX = (M_TILE >= 128) ? 4 : 3;             // activation stages
+    static constexpr int NX = (M_TILE >= 128) ? 4 : 2;             // activation stages
     static constexpr int NS = (M_TILE >= 128) ? 4 : 3;             // scale stages
     static constexpr int X_BYTES = GP * M_TILE * 128;              // [GP][M_TILE][128 B], swizzle-128B
     static constexpr int SX_BYTES = GP * M_TILE * 4;               // f32 [GP][M_TILE]
@@ -73,6 +73,10 @@ struct Cfg {
     static constexpr int NW_FIT = (SMEM_BUDGET - NX * X_BYTES - NS * S_BYTES) / W_BYTES;
     static constexpr int NW = NW_FIT > 10 ? 10 : NW_FIT;
     static_assert(NW >= 3, "too few weight stages");
+    // Two MMA issuer warps take alternate steps.  A ring consumed by the issuers must have an even
+    // number of stages so that each stage is always consumed by the same issuer: an mbarrier parity
+    // wait cannot tell phase p from phase p+2, so an issuer must never skip a phase of a barrier.
+    static_assert(NX % 2 == 0 && NAT % 2 == 0 && NAB % 2 == 0, "issuer-consumed rings need even depth");
     static constexpr int OFF_X = 0;
     static constexpr int OFF_W = OFF_X + NX * X_BYTES;
     static constexpr int OFF_S = OFF_W + NW * W_BYTES;

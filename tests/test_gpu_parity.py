@@ -210,3 +210,56 @@ def test_gemm_ref_layout_dropin(capi, oracle):
     out = capi.gemm_ref_layout(xp, xs, w6, torch.from_numpy(sw).cuda(), M, N, K, xb, ws).cpu().numpy()
     S = oracle.group_sums(xq.astype(np.int32), wq.astype(np.int32))
     _check_close(out, oracle.gemm_exact(S, sx, sw))
+
+
+# ------------------------------------------------------------------------------------------
+# full-size (BASELINE.json shapes): size-independent properties + repeatability
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,xb", [(16, 8192, 8192, 6), (3, 8192, 28672, 8), (200, 4096, 4096, 6), (2048, 1024, 8192, 6)])
+def test_groupsums_full_size_checksum(capi, M, N, K, xb):
+    """sum_g S[m,n,g] must equal the plain integer matmul (computed in float64 on the GPU by torch,
+    exact below 2^53), and every launch must reproduce the same integers."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    xq = torch.randint(-(1 << (xb - 1)), 1 << (xb - 1), (M, K), device="cuda", dtype=torch.int8, generator=g)
+    wq = torch.randint(-32, 32, (N, K), device="cuda", dtype=torch.int8, generator=g)
+    w6 = capi.pack_w6(wq)
+    S = capi.gemm_w6ax_groupsums(xq, w6, N)
+    ref = (xq.double() @ wq.double().t()).round().long()
+    assert torch.equal(S.long().sum(dim=2), ref)
+    # one group checked directly
+    gsel = (K // 128) // 2
+    ref_g = (xq[:, gsel * 128:(gsel + 1) * 128].double() @ wq[:, gsel * 128:(gsel + 1) * 128].double().t()).long()
+    assert torch.equal(S[:, :, gsel].long(), ref_g)
+    for _ in range(3):
+        assert torch.equal(capi.gemm_w6ax_groupsums(xq, w6, N), S)
+
+
+@pytest.mark.parametrize("M,N,K", [(16, 8192, 8192), (8, 8192, 28672), (64, 4096, 11008 // 128 * 128), (256, 2048, 4096)])
+def test_gemm_repeatability_and_linearity(capi, M, N, K):
+    """stress of the pipeline / split-K protocol: 25 back-to-back launches give the same fp16 result
+    (up to the fp32 atomic summation order: <= 1 fp16 ulp), the scratch returns to zero, and scaling
+    the activation scales by 2 doubles the output exactly (linearity in sx)."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    xq = torch.randint(-32, 32, (M, K), device="cuda", dtype=torch.int8, generator=g)
+    wq = torch.randint(-32, 32, (N, K), device="cuda", dtype=torch.int8, generator=g)
+    sx = torch.rand(K // 128, capi.ceil4(M), device="cuda", generator=g) * 0.01 + 1e-3
+    sx = sx.half().float()
+    sw = (torch.rand(K // 128, N, device="cuda", generator=g) * 0.01 + 1e-3).half()
+    w6 = capi.pack_w6(wq)
+    ws = capi.new_workspace()
+    first = capi.gemm_w6ax(xq, sx, w6, sw, N, ws).clone()
+    for _ in range(25):
+        out = capi.gemm_w6ax(xq, sx, w6, sw, N, ws)
+        d = (out.float() - first.float()).abs()
+        assert (d <= first.float().abs() * 2 ** -10 + 1e-6).all()
+    assert not ws.any().item()
+    dbl = capi.gemm_w6ax(xq, sx * 2, w6, sw, N, ws)
+    d = (dbl.float() - 2 * first.float()).abs()
+    assert (d <= first.float().abs() * 2 ** -9 + 1e-6).all()
+    # reference value from exact integer sums (float64 on the GPU)
+    xs = xq.double().view(M, K // 128, 128)
+    wsd = wq.double().view(N, K // 128, 128)
+    S = torch.einsum("mgk,ngk->mng", xs, wsd)
+    ref = (S * sx[:, :M].t().double()[:, None, :] * sw.double().t()[None, :, :]).sum(dim=2)
+    rms = ((first.double() - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt()
+    assert rms <= RMS_REL_TOL, float(rms)
