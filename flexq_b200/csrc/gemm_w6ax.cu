@@ -142,6 +142,11 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = misc[0];
+    if (threadIdx.x == 0) FQ_TRACE(0, 13);
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue / weight
+    // prefetch as our CTAs retire.  Weights are static, so only the roles that touch data produced
+    // by earlier kernels (activations, scales, output, split-K scratch) wait for them below.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // Every role walks the same sequence of steps:
     //   for each segment (tile, [g0,g1)) of this CTA's unit range, for g = g0; g < g1; g += GP
@@ -173,6 +178,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ===================== TMA producer: activation tiles + scale blocks =====================
         reg_dealloc<32>();
         if (lane == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");     // activations / scales come from earlier kernels
             int it = 0;
             for (int u = u_begin; u < u_end;) {
                 const int tile = u / G, g0 = u - tile * G;
@@ -313,6 +319,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
         for (int b = 0; b < C::NAB; b++) mbar_arrive(bar_acc_empty(b));
 
+        asm volatile("griddepcontrol.wait;" ::: "memory");         // D and the split-K scratch belong to earlier kernels until now
         float2 acc[CPT / 2];
         int it = 0;
         for (int u = u_begin; u < u_end;) {
@@ -332,7 +339,29 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_wait(bar_done(it), done_parity(it));
                 if (e == 0) FQ_TRACE(it, 6);
                 tc_fence_after();
-                for (int j = 0; j < ng; j++) {
+                // TMEM drain, software pipelined: the load of chunk c+1 is in flight while chunk c is
+                // dequantised, and the buffer goes back to the MMA issuers as soon as its last chunk has
+                // been read and re-armed -- before that chunk's math.
+                constexpr int NCH = CPT / CH;
+                uint32_t v[2][CH];
+                auto ld_chunk = [&](int j, int c, uint32_t* dst) {
+                    const uint32_t ta = t_lane + ab * C::ACC_COLS + j * M_TILE + c * CH;
+                    if constexpr (CH == 8) tmem_ld8(ta, dst);
+                    else if constexpr (CH == 16) tmem_ld16(ta, dst);
+                    else tmem_ld32(ta, dst);
+                };
+                auto rearm_chunk = [&](int j, int c) {
+                    const uint32_t ta = t_lane + ab * C::ACC_COLS + j * M_TILE + c * CH;
+                    if constexpr (CH == 8) tmem_st8_same(ta, kMagicI);
+                    else {
+#pragma unroll
+                        for (int cc = 0; cc < CH; cc += 16) tmem_st16_same(ta + cc, kMagicI);
+                    }
+                };
+                ld_chunk(0, 0, v[0]);
+#pragma unroll
+                for (int j = 0; j < GP; j++) {           // unrolled: register double-buffer indices stay static
+                    if (j >= ng) break;
                     float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
                     const float* sxs = reinterpret_cast<const float*>(sblk) + j * M_TILE + col0;
                     if (!DUMP) {
@@ -341,46 +370,44 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
                     }
 #pragma unroll
-                    for (int c = 0; c < CPT; c += CH) {
-                        uint32_t v[CH];
-                        const uint32_t ta = t_lane + ab * C::ACC_COLS + j * M_TILE + c;
-                        if constexpr (CH == 8) tmem_ld8(ta, v);
-                        else if constexpr (CH == 16) tmem_ld16(ta, v);
-                        else tmem_ld32(ta, v);
-                        tmem_wait_ld();
-                        // re-arm this chunk of the accumulator for its next use
-                        if constexpr (CH == 8) tmem_st8_same(ta, kMagicI);
-                        else {
-#pragma unroll
-                            for (int cc = 0; cc < CH; cc += 16) tmem_st16_same(ta + cc, kMagicI);
+                    for (int c = 0; c < NCH; c++) {
+                        uint32_t* cur = v[(j * NCH + c) & 1];
+                        uint32_t* nxt = v[(j * NCH + c + 1) & 1];
+                        const bool last_of_step = (c == NCH - 1) && (j == ng - 1);
+                        tmem_wait_ld();                              // chunk (j, c) is in registers
+                        rearm_chunk(j, c);
+                        if (!last_of_step) {
+                            if (c + 1 < NCH) ld_chunk(j, c + 1, nxt);
+                            else ld_chunk(j + 1, 0, nxt);
+                        } else {
+                            tmem_wait_st();                          // every chunk read and re-armed:
+                            tc_fence_before();                       // hand the buffer back before the last math
+                            mbar_arrive(bar_acc_empty(ab));
                         }
                         if constexpr (DUMP) {
                             if (n_ok) {
 #pragma unroll
                                 for (int q = 0; q < CH; q++) {
-                                    const int m = mbase + c + q;
-                                    if (m < p.M) p.S[((size_t)m * p.N + n) * G + g + j] = ((int32_t)(v[q] - kMagicI)) >> 2;
+                                    const int m = mbase + c * CH + q;
+                                    if (m < p.M) p.S[((size_t)m * p.N + n) * G + g + j] = ((int32_t)(cur[q] - kMagicI)) >> 2;
                                 }
                             }
                         } else {
 #pragma unroll
                             for (int q = 0; q < CH; q += 4) {
-                                const float4 s4 = *reinterpret_cast<const float4*>(sxs + c + q);
-                                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(v[q + 0]), __uint_as_float(v[q + 1])), sw2, bias2);
-                                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(v[q + 2]), __uint_as_float(v[q + 3])), sw2, bias2);
-                                acc[(c + q) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c + q) / 2]);
-                                acc[(c + q) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c + q) / 2 + 1]);
+                                const float4 s4 = *reinterpret_cast<const float4*>(sxs + c * CH + q);
+                                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 0]), __uint_as_float(cur[q + 1])), sw2, bias2);
+                                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 2]), __uint_as_float(cur[q + 3])), sw2, bias2);
+                                acc[(c * CH + q) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c * CH + q) / 2]);
+                                acc[(c * CH + q) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c * CH + q) / 2 + 1]);
                             }
                         }
                     }
                 }
-                // accumulators of this step fully read and re-armed: hand the buffer back
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(bar_acc_empty(ab));
                 if (e == 0) FQ_TRACE(it, 7);
                 if (!DUMP) mbar_arrive(bar_s_empty(ss));
             }
+            if (e == 0) FQ_TRACE(it - 1, 10);
             if constexpr (!DUMP) {
                 if (g0 == 0 && g1 == G) {
                     // whole tile reduced by this CTA: store fp16 directly
@@ -399,10 +426,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < CPT; j++) atomicAdd(sl + j * kTileN, (j & 1) ? acc[j / 2].y : acc[j / 2].x);
                     named_bar_sync(1, 256);              // every thread's red.adds are issued ...
-                    if (e == 0) {
-                        __threadfence();                 // ... and released (cumulatively) by one fence
-                        const int old = atomicAdd(p.cnt + slot, g1 - g0);
-                        __threadfence();
+                    if (e == 0) {                        // ... and released (cumulatively) by one acq_rel atomic
+                        int old;
+                        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.cnt + slot), "r"(g1 - g0) : "memory");
                         misc[1] = (old + (g1 - g0) == G) ? 1u : 0u;
                     }
                     named_bar_sync(1, 256);
@@ -420,12 +446,14 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     named_bar_sync(1, 256);              // flag word is reused by the next partial segment
                 }
             }
+            if (e == 0) FQ_TRACE(it - 1, 11);
             u += g1 - g0;
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) FQ_TRACE(0, 12);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -461,6 +489,16 @@ static int num_sms() {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
     }
     return n;
+}
+
+// FLEXQ_PDL=0 disables programmatic dependent launch (A/B experiments)
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FLEXQ_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 struct GemmArgs {
@@ -521,8 +559,17 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
         FLEXQ_CUDA_TRY(cudaFuncSetAttribute(w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
-    w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE><<<P, 512, C::SMEM_BYTES, stream>>>(tmap_x, tmap_sx, tmap_sw, p);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(P);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, tmap_x, tmap_sx, tmap_sw, p);
 }
 
 template <bool DUMP>

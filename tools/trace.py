@@ -15,6 +15,7 @@ ap.add_argument("--m", type=int, default=16)
 ap.add_argument("--n", type=int, default=8192)
 ap.add_argument("--k", type=int, default=8192)
 ap.add_argument("--units", type=int, default=40)
+ap.add_argument("--noflush", action="store_true")
 a = ap.parse_args()
 lib = capi.load()
 dev = torch.device("cuda")
@@ -24,17 +25,24 @@ xq, sx = capi.quant_act(x, 6)
 out = torch.empty(a.m, a.n, dtype=torch.float16, device=dev)
 ws = capi.new_workspace()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for it in range(3):
     tr = torch.zeros(a.units, 16, dtype=torch.int64, device=dev)
-    flush.zero_()
+    if not a.noflush:
+        flush.zero_()
+    else:
+        torch.cuda.synchronize()
+    e0.record()
     capi.check(lib.flexq_debug_gemm_trace(capi._ptr(xq), capi._ptr(sx), capi._ptr(w6), capi._ptr(wsc), capi._ptr(out), a.m, a.n, a.k,
                                           capi._ptr(ws), capi._ptr(tr), a.units, capi._stream()), "trace")
+    e1.record()
     torch.cuda.synchronize()
+    print("launch us", e0.elapsed_time(e1) * 1e3)
 t = tr.cpu().numpy()
 t0 = t[t > 0].min()
-names = ["Wissue", "Wfull", "Aempty", "Afull", "MMArdy", "MMAcmt", "ACCfull", "ACCfree", "EPIend", "Xissue"]
+names = ["Wissue", "Wfull", "Aempty", "Afull", "MMArdy", "MMAcmt", "ACCfull", "ACCfree", "EPIend", "Xissue", "FIXbeg", "FIXend", "END", "START"]
 print("unit " + " ".join(f"{n:>8}" for n in names))
 for i in range(a.units):
-    print(f"{i:4d} " + " ".join(f"{(t[i, e] - t0) if t[i, e] else -1:8d}" for e in range(10)))
+    print(f"{i:4d} " + " ".join(f"{(t[i, e] - t0) if t[i, e] else -1:8d}" for e in range(14)))
 d = np.diff(t[2:, 5])
 print("MMA commit interval cycles: mean %.0f median %.0f" % (d.mean(), np.median(d)))
