@@ -47,7 +47,7 @@ struct GemmParams {
 #define FQ_TRACE(unit, ev)                                                                   \
     do {                                                                                     \
         if constexpr (TRACE) {                                                               \
-            if (blockIdx.x == 0 && (unit) < p.trace_units) p.trace[(unit) * 16 + (ev)] = clock64(); \
+            if (blockIdx.x == (p.trace_units >> 16) && (unit) < (p.trace_units & 0xFFFF)) p.trace[(unit) * 16 + (ev)] = clock64(); \
         }                                                                                    \
     } while (0)
 
@@ -107,6 +107,13 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int P = gridDim.x;
+    if constexpr (TRACE) {     // per-CTA wall-clock window after the step stamps: [trace_units*16 + 2*cta + {0,1}]
+        if (threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[(p.trace_units & 0xFFFF) * 16 + 2 * blockIdx.x] = (long long)t;
+        }
+    }
     const int u_begin = (int)(((long long)blockIdx.x * p.U) / P);
     const int u_end = (int)(((long long)(blockIdx.x + 1) * p.U) / P);
     const int G = p.G;
@@ -434,11 +441,15 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     named_bar_sync(1, 256);
                     const bool last = misc[1] != 0;
                     if (last) {
+                        // all loads first (independent, in flight together), then zero + store:
+                        // interleaving ld/st on the same addresses serialises ~1 us round trips
+#pragma unroll
+                        for (int j = 0; j < CPT / 2; j++) acc[j] = make_float2(__ldcg(sl + (2 * j) * kTileN), __ldcg(sl + (2 * j + 1) * kTileN));
 #pragma unroll
                         for (int j = 0; j < CPT; j++) {
-                            const float vsum = __ldcg(sl + j * kTileN);
                             __stcg(sl + j * kTileN, 0.f);
                             const int m = mbase + j;
+                            const float vsum = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
                             if (n_ok && m < p.M) p.D[(size_t)m * p.N + n] = __float2half_rn(vsum);
                         }
                         if (e == 0) p.cnt[slot] = 0;
@@ -454,6 +465,13 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) FQ_TRACE(0, 12);
+    if constexpr (TRACE) {
+        if (threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            p.trace[(p.trace_units & 0xFFFF) * 16 + 2 * blockIdx.x + 1] = (long long)t;
+        }
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -614,6 +632,9 @@ int gemm_w6ax_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const 
     GemmArgs a = make_args(xq, sx, w6, w_scale, D, nullptr, M, N, K, workspace);
     a.p.trace = trace; a.p.trace_units = trace_units;
     if (M <= 16) return launch<16, 4, false, true>(a, stream);
+    if (M <= 32) return launch<32, 4, false, true>(a, stream);
+    if (M <= 64) return launch<64, 2, false, true>(a, stream);
+    if (M <= 128) return launch<128, 1, false, true>(a, stream);
     return launch<192, 1, false, true>(a, stream);
 }
 
