@@ -81,11 +81,33 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// same, with an L2 eviction-priority hint (createpolicy)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // 2-D tiled TMA load global -> shared
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
         "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst_smem),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {

@@ -38,8 +38,10 @@ struct GemmParams {
     float* slots;            // [kMaxCtas][M_TILE][128] fp32 partial tiles
     int* cnt;                // [kMaxCtas] group counters
     int M, N, K, G;
-    int m_tiles;             // tile index = nt * m_tiles + mt
-    int U;                   // total units
+    int m_tiles, n_tiles;    // tile index = mt * n_tiles + nt: CTAs that run concurrently stream the same weight rows
+                             // (one token tile each), so a weight row is fetched from HBM once and hit in L2 by the rest
+    int Pn, R;               // grid = Pn columns x R rows
+    int tile_gran;           // 1: columns own whole n-tiles (several passes over token tiles)
     long long* trace;        // TRACE builds: [step][16] clock64 stamps of CTA 0
     int trace_units;
 };
@@ -98,7 +100,7 @@ __device__ __forceinline__ int unit_owner(int u, int U, int P) {
 template <int M_TILE, int GP, bool DUMP, bool TRACE>
 __global__ void __launch_bounds__(512, 1)
 w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_sx,
-                 const __grid_constant__ CUtensorMap tmap_sw, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_sw, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     using C = Cfg<M_TILE, GP>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -114,9 +116,16 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             p.trace[(p.trace_units & 0xFFFF) * 16 + 2 * blockIdx.x] = (long long)t;
         }
     }
-    const int u_begin = (int)(((long long)blockIdx.x * p.U) / P);
-    const int u_end = (int)(((long long)(blockIdx.x + 1) * p.U) / P);
     const int G = p.G;
+    // CTA = (column j, row r): row r owns token tiles mt = r, r+R, ...; the Pn columns split the
+    // (n-tile, k-group) units of a token tile into the same contiguous ranges for every row, so
+    // the CTAs of a column stream identical weight tiles at the same time (one HBM fetch, L2 hits
+    // for the rest).  With a single pass the split is at group granularity (stream-K, partial tiles
+    // reduced through the scratch); with several passes it is at tile granularity (no partial tiles).
+    const int cta_j = blockIdx.x % p.Pn, cta_r = blockIdx.x / p.Pn;
+    const int Umt = p.n_tiles * G;
+    const int u_begin = p.tile_gran ? (int)(((long long)cta_j * p.n_tiles) / p.Pn) * G : (int)(((long long)cta_j * Umt) / p.Pn);
+    const int u_end = p.tile_gran ? (int)(((long long)(cta_j + 1) * p.n_tiles) / p.Pn) * G : (int)(((long long)(cta_j + 1) * Umt) / p.Pn);
 
     // full/empty rings.  One tcgen05.commit per step arrives on bar_done(step % NDONE); it frees the
     // activation stage and the TMEM weight stage of that step and publishes its accumulators.
@@ -163,11 +172,15 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ===================== TMA producer: packed weight tiles =====================
         reg_dealloc<32>();
         if (lane == 0) {
+            // weights are read once when there is a single token tile (decode): keep them from
+            // displacing activations/scales in L2; with several token tiles the same weight row is
+            // re-streamed per token tile and should stay resident
+            const uint64_t pol = (p.m_tiles == 1) ? l2_policy_evict_first() : l2_policy_evict_last();
             int it = 0;
+            for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
             for (int u = u_begin; u < u_end;) {
-                const int tile = u / G, g0 = u - tile * G;
+                const int nt = u / G, g0 = u - nt * G;
                 const int g1 = min(G, g0 + (u_end - u));
-                const int nt = tile / p.m_tiles;
                 const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
                 for (int g = g0; g < g1; g += GP, it++) {
                     const int ng = min(GP, g1 - g);
@@ -175,7 +188,15 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     mbar_wait(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
                     FQ_TRACE(it, 0);
                     mbar_expect_tx(bar_w_full(s), ng * kTileBytes);
-                    bulk_g2s(smem_base + C::OFF_W + s * C::W_BYTES, wsrc + (size_t)g * kTileBytes, ng * kTileBytes, bar_w_full(s));
+                    if (p.m_tiles == 1) {
+                        bulk_g2s_hint(smem_base + C::OFF_W + s * C::W_BYTES, wsrc + (size_t)g * kTileBytes, ng * kTileBytes, bar_w_full(s), pol);
+                    } else {
+                        // re-streamed weights go through tensor-map TMA loads (W6 seen as [bytes/128][128]); measured:
+                        // plain bulk copies never hit in L2 on the second pass, tiled loads do
+                        for (int j = 0; j < ng; j++)
+                            tma_load_2d_hint(smem_base + C::OFF_W + s * C::W_BYTES + j * kTileBytes, &tmap_w, 0,
+                                             (nt * G + g + j) * (kTileBytes / 128), bar_w_full(s), pol);
+                    }
                 }
                 u += g1 - g0;
             }
@@ -186,11 +207,12 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         reg_dealloc<32>();
         if (lane == 0) {
             asm volatile("griddepcontrol.wait;" ::: "memory");     // activations / scales come from earlier kernels
+            const uint64_t pol_x = l2_policy_evict_last();          // every n-tile re-reads the activations: keep them in L2
             int it = 0;
+            for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
             for (int u = u_begin; u < u_end;) {
-                const int tile = u / G, g0 = u - tile * G;
+                const int nt = u / G, g0 = u - nt * G;
                 const int g1 = min(G, g0 + (u_end - u));
-                const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
                 for (int g = g0; g < g1; g += GP, it++) {
                     {   // [ng][M_TILE][128 B] swizzle-128B tiles, one TMA per k-group; rows >= M are zero-filled
                         const int ng = min(GP, g1 - g);
@@ -199,8 +221,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         FQ_TRACE(it, 9);
                         mbar_expect_tx(bar_x_full(s), ng * (M_TILE * 128));
                         for (int j = 0; j < ng; j++)
-                            tma_load_2d(smem_base + C::OFF_X + s * C::X_BYTES + j * (M_TILE * 128), &tmap_x, (g + j) * kGroup, mt * M_TILE,
-                                        bar_x_full(s));
+                            tma_load_2d_hint(smem_base + C::OFF_X + s * C::X_BYTES + j * (M_TILE * 128), &tmap_x, (g + j) * kGroup, mt * M_TILE,
+                                             bar_x_full(s), pol_x);
                     }
                     if (!DUMP) {   // sx[g..g+GP][m0..] (f32) and w_scale[g..g+GP][n0..] (f16)
                         const int s = it % C::NS;
@@ -221,8 +243,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
             int it = 0;
+            for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
             for (int u = u_begin; u < u_end;) {
-                const int tile = u / G, g0 = u - tile * G;
+                const int nt = u / G, g0 = u - nt * G;
                 const int g1 = min(G, g0 + (u_end - u));
                 for (int g = g0; g < g1; g += GP, it++) {
                     if ((it & 1) != (warp - 1)) continue;
@@ -262,8 +285,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int r = threadIdx.x - 128;                 // weight row within the tile == TMEM lane
         const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0;
         int it = 0;
-        for (int u = u_begin; u < u_end;) {
-            const int tile = u / G, g0 = u - tile * G;
+        for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
+            for (int u = u_begin; u < u_end;) {
+            const int nt = u / G, g0 = u - nt * G;
             const int g1 = min(G, g0 + (u_end - u));
             for (int g = g0; g < g1; g += GP, it++) {
                 const int ng = min(GP, g1 - g);
@@ -329,10 +353,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         asm volatile("griddepcontrol.wait;" ::: "memory");         // D and the split-K scratch belong to earlier kernels until now
         float2 acc[CPT / 2];
         int it = 0;
-        for (int u = u_begin; u < u_end;) {
-            const int tile = u / G, g0 = u - tile * G;
+        for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
+            for (int u = u_begin; u < u_end;) {
+            const int nt = u / G, g0 = u - nt * G;
             const int g1 = min(G, g0 + (u_end - u));
-            const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
             const int n = nt * kTileN + r;
             const int mbase = mt * M_TILE + col0;
             const bool n_ok = n < p.N;
@@ -423,12 +447,12 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         for (int j = 0; j < CPT; j++) {
                             const int m = mbase + j;
                             const float a = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
-                            if (m < p.M) p.D[(size_t)m * p.N + n] = __float2half_rn(a);
+                            if (m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n, __half_as_ushort(__float2half_rn(a)));   // streaming: do not displace X/W in L2
                         }
                     }
                 } else {
                     // partial tile: accumulate in the slot owned by the tile's first CTA
-                    const int slot = unit_owner(tile * G, p.U, P);
+                    const int slot = cta_r * p.Pn + unit_owner(nt * G, Umt, p.Pn);   // single pass: (row, first column of the tile) is unique
                     float* sl = p.slots + (size_t)slot * kSlotFloats + (size_t)col0 * kTileN + r;
 #pragma unroll
                     for (int j = 0; j < CPT; j++) atomicAdd(sl + j * kTileN, (j & 1) ? acc[j / 2].y : acc[j / 2].x);
@@ -450,7 +474,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             __stcg(sl + j * kTileN, 0.f);
                             const int m = mbase + j;
                             const float vsum = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
-                            if (n_ok && m < p.M) p.D[(size_t)m * p.N + n] = __float2half_rn(vsum);
+                            if (n_ok && m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n, __half_as_ushort(__float2half_rn(vsum)));
                         }
                         if (e == 0) p.cnt[slot] = 0;
                     }
@@ -536,7 +560,17 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     if (!enc || sms <= 0) return FLEXQ_ERR_NO_DEVICE;
     const cuuint32_t ones[3] = {1u, 1u, 1u};
 
-    CUtensorMap tmap_x, tmap_sx, tmap_sw;
+    CUtensorMap tmap_x, tmap_sx, tmap_sw, tmap_w;
+    {   // packed weights as a [total_bytes/128][128 B] byte matrix: one tile = 96 consecutive rows
+        const cuuint64_t rows = (cuuint64_t)ceil_div(p.N, kTileN) * p.G * (kTileBytes / 128);
+        const cuuint64_t dims[2] = {128u, rows};
+        const cuuint64_t strides[1] = {128u};
+        const cuuint32_t box[2] = {128u, (cuuint32_t)(kTileBytes / 128)};
+        if (enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(p.w6), dims, strides, box, ones,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FLEXQ_ERR_TENSORMAP;
+    }
     {   // activations [M][K] int8, box = 128 bytes of k x M_TILE tokens, 128-byte swizzle
         const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
         const cuuint64_t strides[1] = {(cuuint64_t)p.K};
@@ -567,10 +601,22 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
         tmap_sw = tmap_x;
     }
 
-    const int n_tiles = ceil_div(p.N, kTileN);
+    p.n_tiles = ceil_div(p.N, kTileN);
     p.m_tiles = ceil_div(p.M, M_TILE);
-    p.U = n_tiles * p.m_tiles * p.G;
-    const int P = p.U < sms ? p.U : (sms < kMaxCtas ? sms : kMaxCtas);
+    {   // pick R rows x Pn columns minimising the per-CTA work (in k-group units); ties -> more rows (more sharing)
+        const int max_ctas = sms < kMaxCtas ? sms : kMaxCtas;
+        const long long Umt = (long long)p.n_tiles * p.G;
+        long long best = -1;
+        for (int R = 1; R <= p.m_tiles && R <= max_ctas; R++) {
+            long long Pn = max_ctas / R;
+            const int passes = ceil_div(p.m_tiles, R);
+            long long cost;
+            if (passes == 1) { if (Pn > Umt) Pn = Umt; cost = (Umt + Pn - 1) / Pn; }
+            else { if (Pn > p.n_tiles) Pn = p.n_tiles; cost = (long long)passes * ((p.n_tiles + Pn - 1) / Pn) * p.G; }
+            if (best < 0 || cost <= best) { best = cost; p.R = R; p.Pn = (int)Pn; p.tile_gran = passes > 1; }
+        }
+    }
+    const int P = p.Pn * p.R;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -587,7 +633,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, tmap_x, tmap_sx, tmap_sw, p);
+    return (int)cudaLaunchKernelEx(&cfg, w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, tmap_x, tmap_sx, tmap_sw, tmap_w, p);
 }
 
 template <bool DUMP>
