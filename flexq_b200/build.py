@@ -9,7 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libflexq_b200.so")
 SOURCES = ["capi.cu", "act_quant.cu", "weight_pack.cu", "planes.cu", "gemm_w6ax.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "flexq_b200.h")]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+EXTRA = os.environ.get("FLEXQ_NVCC_EXTRA", "").split()
+NVCC_FLAGS = [*EXTRA, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 

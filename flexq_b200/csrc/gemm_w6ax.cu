@@ -87,10 +87,28 @@ struct Cfg {
     static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_MISC + 16 + 1024;        // + alignment slack
-    static constexpr int CPT = M_TILE / 2;                         // columns per epilogue thread
-    static constexpr int CH = CPT < 32 ? CPT : 32;                 // columns per tcgen05.ld
+    // epilogue warpgroups (2 or 4).  Measured on B200: 4 warpgroups (16 warps, 96 regs) give the same
+    // prefill throughput as 2 (8 warps, 200 regs) -- the epilogue is bound by issue slots / FMA-heavy
+    // pipe, not by latency hiding -- so the simpler 512-thread shape is used everywhere.
+    static constexpr int EPI_WG = 2;
+    static constexpr int EPI_THREADS = 128 * EPI_WG;
+    static constexpr int THREADS = 256 + EPI_THREADS;
+    // setmaxnreg pool = registers the CTA is launched with (regs/thread x THREADS, 80 x 768 or 128 x 512):
+    //   768 threads: 128*32 + 128*64 + 512*96  = 61440;   512 threads: 128*32 + 128*72 + 256*200 = 64512
+    static constexpr int EPI_REGS = (EPI_WG == 4) ? 96 : 200;
+    static constexpr int EXP_REGS = (EPI_WG == 4) ? 64 : 72;
+    static constexpr int CPT = M_TILE / EPI_WG;                    // columns per epilogue thread
+    static constexpr int CH = (EPI_WG == 4) ? 16 : (CPT < 32 ? CPT : 32);   // columns per tcgen05.ld
     static_assert(CPT % CH == 0 && (CH == 8 || CH == 16 || CH == 32), "epilogue chunking");
 };
+
+// Accumulator biasing strategy.  true: the epilogue re-arms TMEM with the bit pattern of 1.5*2^23 after
+// every read (tcgen05.st) and all MMAs accumulate; false: the first MMA of a group overwrites
+// (accumulate = 0) and the epilogue adds the bias with one integer add per element.
+#ifndef FLEXQ_REARM
+#define FLEXQ_REARM 0
+#endif
+constexpr bool kRearm = FLEXQ_REARM != 0;
 
 // owner(u) = the CTA whose unit range [floor(c*U/P), floor((c+1)*U/P)) contains u
 __device__ __forceinline__ int unit_owner(int u, int U, int P) {
@@ -98,7 +116,7 @@ __device__ __forceinline__ int unit_owner(int u, int U, int P) {
 }
 
 template <int M_TILE, int GP, bool DUMP, bool TRACE>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(Cfg<M_TILE, GP>::THREADS, 1)
 w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_sx,
                  const __grid_constant__ CUtensorMap tmap_sw, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     using C = Cfg<M_TILE, GP>;
@@ -145,8 +163,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         for (int s = 0; s < C::NAT; s++) mbar_init(bar_a_full(s), 128);
         for (int s = 0; s < C::NX; s++) mbar_init(bar_x_full(s), 1);
         for (int s = 0; s < C::NW; s++) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 128); }
-        for (int s = 0; s < C::NS; s++) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), 256); }
-        for (int b = 0; b < C::NAB; b++) mbar_init(bar_acc_empty(b), 256);
+        for (int s = 0; s < C::NS; s++) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), C::EPI_THREADS); }
+        for (int b = 0; b < C::NAB; b++) mbar_init(bar_acc_empty(b), C::EPI_THREADS);
         for (int i = 0; i < C::NDONE; i++) mbar_init(bar_done(i), 1);
         fence_barrier_init();
         prefetch_tensormap(&tmap_x);
@@ -270,7 +288,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                             umma_i8_ts(d_tmem + j * M_TILE, a_tmem + j * 32 + 8 * k,
-                                       umma_desc_sw128(b_addr + j * (M_TILE * 128) + 32 * k), idesc, 1u);
+                                       umma_desc_sw128(b_addr + j * (M_TILE * 128) + 32 * k), idesc, (kRearm || k > 0) ? 1u : 0u);
                     }
                     umma_commit(bar_done(it));
                     FQ_TRACE(it, 5);
@@ -281,7 +299,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         __syncwarp();
     } else if (warp < 8) {
         // ===================== weight expanders: smem (packed) -> registers -> TMEM (int8) =====================
-        reg_dealloc<72>();
+        reg_dealloc<C::EXP_REGS>();
         const int r = threadIdx.x - 128;                 // weight row within the tile == TMEM lane
         const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0;
         int it = 0;
@@ -326,27 +344,29 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // int32 sum 4*S read back from TMEM *is* the float (kMagicF + 4*S): one FMA with the
         // per-row weight scale removes the bias exactly (kMagicF*sw is exact in fp32 for an
         // fp16-valued sw) and a second FMA applies the per-token scale and accumulates.
-        reg_alloc<200>();
+        reg_alloc<C::EPI_REGS>();
         constexpr int CPT = C::CPT, CH = C::CH;
         constexpr uint32_t kMagicI = 0x4B400000u;
         constexpr float kMagicF = 12582912.f;
         const int e = threadIdx.x - 256;
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-        const int half_id = e >> 7;
+        const int wg_id = e >> 7;                        // which CPT-column slice of the token tile
         const int r = quad * 32 + lane;
-        const int col0 = half_id * CPT;
+        const int col0 = wg_id * CPT;
         const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + col0;
         // arm every accumulator buffer once
+        if constexpr (kRearm) {
 #pragma unroll
-        for (int b = 0; b < C::NAB * GP; b++) {
+            for (int b = 0; b < C::NAB * GP; b++) {
 #pragma unroll
-            for (int c = 0; c < CPT; c += (CPT < 16 ? 8 : 16)) {
-                if constexpr (CPT < 16) tmem_st8_same(t_lane + b * M_TILE + c, kMagicI);
-                else tmem_st16_same(t_lane + b * M_TILE + c, kMagicI);
+                for (int c = 0; c < CPT; c += (CPT < 16 ? 8 : 16)) {
+                    if constexpr (CPT < 16) tmem_st8_same(t_lane + b * M_TILE + c, kMagicI);
+                    else tmem_st16_same(t_lane + b * M_TILE + c, kMagicI);
+                }
             }
+            tmem_wait_st();
+            tc_fence_before();
         }
-        tmem_wait_st();
-        tc_fence_before();
 #pragma unroll
         for (int b = 0; b < C::NAB; b++) mbar_arrive(bar_acc_empty(b));
 
@@ -389,10 +409,19 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         for (int cc = 0; cc < CH; cc += 16) tmem_st16_same(ta + cc, kMagicI);
                     }
                 };
+#ifdef FLEXQ_EXP_NOEPI
+                // experiment: upper bound of the producer/expander/MMA side (no TMEM drain, results invalid)
+                tc_fence_before();
+                mbar_arrive(bar_acc_empty(ab));
+                if (false)
+#endif
                 ld_chunk(0, 0, v[0]);
 #pragma unroll
                 for (int j = 0; j < GP; j++) {           // unrolled: register double-buffer indices stay static
                     if (j >= ng) break;
+#ifdef FLEXQ_EXP_NOEPI
+                    break;
+#endif
                     float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
                     const float* sxs = reinterpret_cast<const float*>(sblk) + j * M_TILE + col0;
                     if (!DUMP) {
@@ -406,12 +435,12 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         uint32_t* nxt = v[(j * NCH + c + 1) & 1];
                         const bool last_of_step = (c == NCH - 1) && (j == ng - 1);
                         tmem_wait_ld();                              // chunk (j, c) is in registers
-                        rearm_chunk(j, c);
+                        if constexpr (kRearm) rearm_chunk(j, c);
                         if (!last_of_step) {
                             if (c + 1 < NCH) ld_chunk(j, c + 1, nxt);
                             else ld_chunk(j + 1, 0, nxt);
                         } else {
-                            tmem_wait_st();                          // every chunk read and re-armed:
+                            if constexpr (kRearm) tmem_wait_st();    // every chunk read (and re-armed):
                             tc_fence_before();                       // hand the buffer back before the last math
                             mbar_arrive(bar_acc_empty(ab));
                         }
@@ -420,15 +449,16 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                                 for (int q = 0; q < CH; q++) {
                                     const int m = mbase + c * CH + q;
-                                    if (m < p.M) p.S[((size_t)m * p.N + n) * G + g + j] = ((int32_t)(cur[q] - kMagicI)) >> 2;
+                                    if (m < p.M) p.S[((size_t)m * p.N + n) * G + g + j] = ((int32_t)(kRearm ? cur[q] - kMagicI : cur[q])) >> 2;
                                 }
                             }
                         } else {
 #pragma unroll
                             for (int q = 0; q < CH; q += 4) {
                                 const float4 s4 = *reinterpret_cast<const float4*>(sxs + c * CH + q);
-                                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 0]), __uint_as_float(cur[q + 1])), sw2, bias2);
-                                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 2]), __uint_as_float(cur[q + 3])), sw2, bias2);
+                                constexpr uint32_t kAdd = kRearm ? 0u : kMagicI;   // int32 4S -> bits of the float (kMagicF + 4S)
+                                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 0] + kAdd), __uint_as_float(cur[q + 1] + kAdd)), sw2, bias2);
+                                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 2] + kAdd), __uint_as_float(cur[q + 3] + kAdd)), sw2, bias2);
                                 acc[(c * CH + q) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c * CH + q) / 2]);
                                 acc[(c * CH + q) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c * CH + q) / 2 + 1]);
                             }
@@ -456,13 +486,13 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     float* sl = p.slots + (size_t)slot * kSlotFloats + (size_t)col0 * kTileN + r;
 #pragma unroll
                     for (int j = 0; j < CPT; j++) atomicAdd(sl + j * kTileN, (j & 1) ? acc[j / 2].y : acc[j / 2].x);
-                    named_bar_sync(1, 256);              // every thread's red.adds are issued ...
+                    named_bar_sync(1, C::EPI_THREADS);              // every thread's red.adds are issued ...
                     if (e == 0) {                        // ... and released (cumulatively) by one acq_rel atomic
                         int old;
                         asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.cnt + slot), "r"(g1 - g0) : "memory");
                         misc[1] = (old + (g1 - g0) == G) ? 1u : 0u;
                     }
-                    named_bar_sync(1, 256);
+                    named_bar_sync(1, C::EPI_THREADS);
                     const bool last = misc[1] != 0;
                     if (last) {
                         // all loads first (independent, in flight together), then zero + store:
@@ -478,7 +508,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         }
                         if (e == 0) p.cnt[slot] = 0;
                     }
-                    named_bar_sync(1, 256);              // flag word is reused by the next partial segment
+                    named_bar_sync(1, C::EPI_THREADS);              // flag word is reused by the next partial segment
                 }
             }
             if (e == 0) FQ_TRACE(it - 1, 11);
@@ -625,7 +655,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(P);
-    cfg.blockDim = dim3(512);
+    cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
