@@ -60,6 +60,10 @@ __device__ __forceinline__ float quant8(const uint4& raw, int bits, int* q) {
 template <int MODE>
 __global__ void __launch_bounds__(256) quant_act_native_kernel(const uint4* __restrict__ x, int8_t* __restrict__ xq,
                                                                float* __restrict__ sx, int M, int K, int ldsx, int bits) {
+    // programmatic dependent launch: the GEMM that consumes Xq/sx may start streaming its weights now;
+    // this kernel itself waits for the producer of X (no-ops when launched without the attribute)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int G = K / kGroup;
     const long long vec = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // 8-half vector index
     const long long grp = vec >> 4;                                           // (row, group) index
@@ -122,11 +126,18 @@ int quant_act_native(const __half* x, int8_t* xq, float* sx, int M, int K, int b
     const int ldsx = ceil4(M);
     const long long threads = (long long)ldsx * (K / kGroup) * 16;
     const int blocks = (int)((threads + 255) / 256);
-    if (mode == FLEXQ_ROUND_PYTHON)
-        quant_act_native_kernel<FLEXQ_ROUND_PYTHON><<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), xq, sx, M, K, ldsx, bits);
-    else
-        quant_act_native_kernel<FLEXQ_ROUND_CUDA><<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), xq, sx, M, K, ldsx, bits);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    if (mode == FLEXQ_ROUND_PYTHON) return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_PYTHON>, xv, xq, sx, M, K, ldsx, bits);
+    return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_CUDA>, xv, xq, sx, M, K, ldsx, bits);
 }
 
 int quant_act_planes(const __half* x, uint32_t* planes, __half* xs, int M, int K, int bits, cudaStream_t stream) {

@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Synthetic-weight decode of a LLaMA linear stack (BASELINE.json configs[3]: LLaMA-3-8B, mixed
+W6A6 / W6A8 per the reference's --flex_linear_quant policy: down_proj gets 8-bit activations,
+algorithm/models/int_llama_layer.py:31-43).
+
+Every decoder layer's linears (qkv, o, gate, up, down) run through the fused flexq_b200 path
+(activation quantise + W6Ax GEMM), all layers with their own weights, captured in one CUDA graph.
+tok/s = batch / time of one pass over the stack.  Attention, KV cache, norms and sampling are NOT
+included -- this measures the quantised-linear hot path only.  Printed beside the same stack in
+cuBLAS FP16 (torch.matmul)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from flexq_b200 import capi  # noqa: E402
+
+MODELS = {
+    # hidden, intermediate, qkv_out, layers
+    "llama3-8b": (4096, 14336, 6144, 32),
+    "llama2-7b": (4096, 11008, 12288, 32),
+    "llama2-70b": (8192, 28672, 10240, 80),
+}
+
+
+def graph_us(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3)
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="llama3-8b")
+    ap.add_argument("--batches", default="1,2,4,8,16")
+    ap.add_argument("--layers", type=int, default=0, help="override layer count (memory)")
+    ap.add_argument("--fuse-gate-up", action="store_true", help="gate and up as one N=2*inter GEMM")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    hid, inter, qkv, layers = MODELS[a.model]
+    layers = a.layers or layers
+    dev = torch.device("cuda")
+    capi.load()
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    shapes = [("qkv", qkv, hid, 6), ("o", hid, hid, 6)]
+    shapes += [("gate_up", 2 * inter, hid, 6)] if a.fuse_gate_up else [("gate", inter, hid, 6), ("up", inter, hid, 6)]
+    shapes += [("down", hid, inter, 8)]
+    packed, fp16 = [], []
+    for _ in range(layers):
+        lw, lf = [], []
+        for name, N, K, xb in shapes:
+            w = (0.02 * torch.randn(N, K, device=dev)).half()
+            w6, ws = capi.quant_pack_w6(w)
+            lw.append((w6, ws, N, K, xb))
+            lf.append(w)
+        packed.append(lw)
+        fp16.append(lf)
+    wbytes = sum(N * K * 6 // 8 + N * (K // 128) * 2 for _, N, K, _ in shapes) * layers
+    results = []
+    for B in [int(b) for b in a.batches.split(",")]:
+        xs = {K: torch.randn(B, K, device=dev).half() for _, _, K, _ in shapes}
+        outs = {(N, K): torch.empty(B, N, dtype=torch.float16, device=dev) for _, N, K, _ in shapes}
+        wss = {K: capi.new_workspace(B, K) for _, _, K, _ in shapes}
+
+        def run_q():
+            for lw in packed:
+                for w6, ws, N, K, xb in lw:
+                    capi.linear_w6ax(xs[K], w6, ws, N, xb, wss[K], capi.ROUND_CUDA, outs[(N, K)])
+
+        def run_f():
+            for lf in fp16:
+                for w in lf:
+                    torch.matmul(xs[w.shape[1]], w.t(), out=outs[(w.shape[0], w.shape[1])])
+
+        tq, tf = graph_us(run_q), graph_us(run_f)
+        rec = {"model": a.model, "layers": layers, "batch": B, "fuse_gate_up": a.fuse_gate_up, "linears_per_layer": len(shapes),
+               "w6ax_us": tq, "w6ax_tok_s": B / tq * 1e6, "fp16_us": tf, "fp16_tok_s": B / tf * 1e6, "speedup_vs_fp16": tf / tq,
+               "weight_gbs": wbytes / tq / 1e3, "hbm_frac": wbytes / tq / 1e3 / hbm,
+               "note": "linear stack only (no attention / KV / norms); synthetic weights"}
+        results.append(rec)
+        print(json.dumps(rec), flush=True)
+    if a.out:
+        os.makedirs(os.path.dirname(a.out), exist_ok=True)
+        with open(a.out, "w") as f:
+            for r in results:
+                f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()
