@@ -281,14 +281,17 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                     FQ_TRACE(it, 4);
                     tc_fence_after();
-                    const uint32_t b_addr = smem_base + C::OFF_X + sx_ * C::X_BYTES;
+                    // descriptor of the stage base once; per MMA only the 16-byte-unit address field advances
+                    const uint64_t b_desc0 = umma_desc_sw128(smem_base + C::OFF_X + sx_ * C::X_BYTES);
                     const uint32_t d_tmem = tmem_base + ab * C::ACC_COLS;
                     const uint32_t a_tmem = tmem_base + C::A_COL0 + st * C::A_COLS;
-                    for (int j = 0; j < ng; j++) {
+#pragma unroll
+                    for (int j = 0; j < GP; j++) {
+                        if (j >= ng) break;
 #pragma unroll
                         for (int k = 0; k < 4; k++)
                             umma_i8_ts(d_tmem + j * M_TILE, a_tmem + j * 32 + 8 * k,
-                                       umma_desc_sw128(b_addr + j * (M_TILE * 128) + 32 * k), idesc, (kRearm || k > 0) ? 1u : 0u);
+                                       b_desc0 + (uint64_t)((j * (M_TILE * 128) + 32 * k) >> 4), idesc, (kRearm || k > 0) ? 1u : 0u);
                     }
                     umma_commit(bar_done(it));
                     FQ_TRACE(it, 5);
