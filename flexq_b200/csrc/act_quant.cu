@@ -34,10 +34,20 @@ __device__ __forceinline__ float quant8(const uint4& raw, int bits, int* q) {
     if (MODE == FLEXQ_ROUND_CUDA) {
         const float s = __fdiv_rn(amax, (float)hi);                     // bit_packing.cu:151
         r = __half2float(__float2half_rn(s));                           // :155,:158
+        // round(x / r) with IEEE division is the reference's arithmetic (:160).  x * (1/r) is within
+        // 2 ulp of x / r, so it rounds to the same integer unless it lands within 1e-4 of a .5 tie;
+        // only then (and for r == 0 / non-finite values) is the exact division evaluated.
+        const float rcp = __frcp_rn(r);
+        const bool plain = r > 0.f && rcp < 3.0e38f;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float t = roundf(__fdiv_rn(xf[i], r));                // :160 (half away from zero)
-            const int v = __float2int_rz(t);                            // NaN -> 0, saturating
+            const float t = xf[i] * rcp;
+            const float fr = fabsf(t - truncf(t));
+            int v;
+            if (!plain || fabsf(fr - 0.5f) < 1e-4f || !(fabsf(t) < 1e6f))
+                v = __float2int_rz(roundf(__fdiv_rn(xf[i], r)));        // half away from zero; NaN -> 0, saturating
+            else
+                v = __float2int_rz(t + copysignf(0.5f, t));             // same integer: t is >= 1e-4 away from a tie
             q[i] = max(lo, min(hi, v));
         }
     } else {

@@ -263,3 +263,36 @@ def test_gemm_repeatability_and_linearity(capi, M, N, K):
     ref = (S * sx[:, :M].t().double()[:, None, :] * sw.double().t()[None, :, :]).sum(dim=2)
     rms = ((first.double() - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt()
     assert rms <= RMS_REL_TOL, float(rms)
+
+
+# ------------------------------------------------------------------------------------------
+# the python drop-in module against the reference module's own golden outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["lin_w6a6_f16", "lin_w6a8_f16"])
+def test_quantlinear_module_vs_reference_golden(capi, case):
+    """flexq_b200.QuantLinear (CUDA path) on the inputs of tests/golden/linear_golden.npz, which holds
+    the outputs of the reference's own QuantLinear (algorithm/flexq_quantize/int_linear.py) in fp16."""
+    import os
+    import torch.nn as nn
+    from flexq_b200 import QuantLinear
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "linear_golden.npz"))
+    w, x, y_ref = g[case + "/w"], g[case + "/x"], g[case + "/y"]
+    ab = int(g[case + "/abits"])
+    lin = nn.Linear(w.shape[1], w.shape[0], bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(w.astype(np.float32)))
+    lin = lin.half().cuda()
+    p = dict(n_bits=6, per_channel_axes=[0], symmetric=True, dynamic_method="per_group", group_size=128, disable_zero_point=True)
+    ql = QuantLinear(lin, p, dict(p, n_bits=ab, per_channel_axes=[]), act_round=capi.ROUND_PYTHON)
+    ql.set_quant_state(True, True)
+    assert ql.kernel_supported()
+    y = ql(torch.from_numpy(x).cuda())
+    # weights: same integers and scales as the reference's fake-quantised weight
+    w6, wsc = ql.pack_weights()
+    wq = capi.w6_to_i8(w6, w.shape[0], w.shape[1]).cpu().numpy().astype(np.float32)
+    wdeq = wq.reshape(w.shape[0], -1, 128) * wsc.cpu().numpy().astype(np.float32).T[:, :, None]
+    assert np.array_equal(wdeq.reshape(w.shape).astype(np.float16), g[case + "/wdeq"])
+    _check_close(y.cpu().numpy(), y_ref)
+    # 3-D input [1, S, K] as the reference's decoder layers pass it (quantizer.py:100-103)
+    y3 = ql(torch.from_numpy(x).cuda().unsqueeze(0))
+    assert y3.shape == (1, x.shape[0], w.shape[0]) and torch.equal(y3[0], y)
