@@ -399,6 +399,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 constexpr int NCH = CPT / CH;
                 uint32_t v[2][CH];
                 auto ld_chunk = [&](int j, int c, uint32_t* dst) {
+#ifdef FLEXQ_EXP_NOLD
+                    for (int q = 0; q < CH; q++) dst[q] = (uint32_t)(j + c + q + it);   // experiment: no TMEM traffic
+                    return;
+#endif
                     const uint32_t ta = t_lane + ab * C::ACC_COLS + j * M_TILE + c * CH;
                     if constexpr (CH == 8) tmem_ld8(ta, dst);
                     else if constexpr (CH == 16) tmem_ld16(ta, dst);
@@ -437,7 +441,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         uint32_t* cur = v[(j * NCH + c) & 1];
                         uint32_t* nxt = v[(j * NCH + c + 1) & 1];
                         const bool last_of_step = (c == NCH - 1) && (j == ng - 1);
+#ifndef FLEXQ_EXP_NOLD
                         tmem_wait_ld();                              // chunk (j, c) is in registers
+#endif
                         if constexpr (kRearm) rearm_chunk(j, c);
                         if (!last_of_step) {
                             if (c + 1 < NCH) ld_chunk(j, c + 1, nxt);
@@ -456,6 +462,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                 }
                             }
                         } else {
+#ifdef FLEXQ_EXP_NOMATH
+                            acc[0].x += __uint_as_float(cur[0] ^ cur[CH - 1]);   // experiment: drain only
+                            if (false)
+#endif
 #pragma unroll
                             for (int q = 0; q < CH; q += 4) {
                                 const float4 s4 = *reinterpret_cast<const float4*>(sxs + c * CH + q);
