@@ -686,6 +686,12 @@ static int dispatch(const GemmArgs& a, cudaStream_t stream) {
     if (M <= 32) return launch<32, 4, DUMP>(a, stream);
     if (M <= 64) return launch<64, 2, DUMP>(a, stream);
     if (M <= 128) return launch<128, 1, DUMP>(a, stream);
+    // token tile for large M: 192 (fewer weight expansions per MMA) unless 128 wastes fewer padded rows
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("FLEXQ_MTILE"); force = e ? atoi(e) : 0; }
+    const int pad192 = ceil_div(M, 192) * 192 - M, pad128 = ceil_div(M, 128) * 128 - M;
+    const bool use128 = force ? force == 128 : (pad128 * 4 < pad192 * 3 && pad192 * 16 > M);
+    if (use128) return launch<128, 1, DUMP>(a, stream);
     return launch<192, 1, DUMP>(a, stream);
 }
 
