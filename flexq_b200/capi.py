@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflexq_b200.so")
+LIB_PATH = os.environ.get("FLEXQ_B200_LIB") or os.path.join(_HERE, "libflexq_b200.so")
 
 GROUP = 128
 ROUND_CUDA = 0

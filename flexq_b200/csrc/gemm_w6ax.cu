@@ -90,7 +90,10 @@ struct Cfg {
     // epilogue warpgroups (2 or 4).  Measured on B200: 4 warpgroups (16 warps, 96 regs) give the same
     // prefill throughput as 2 (8 warps, 200 regs) -- the epilogue is bound by issue slots / FMA-heavy
     // pipe, not by latency hiding -- so the simpler 512-thread shape is used everywhere.
-    static constexpr int EPI_WG = 2;
+#ifndef FLEXQ_EPI_WG
+#define FLEXQ_EPI_WG 2
+#endif
+    static constexpr int EPI_WG = (FLEXQ_EPI_WG == 4 && M_TILE >= 128) ? 4 : 2;
     static constexpr int EPI_THREADS = 128 * EPI_WG;
     static constexpr int THREADS = 256 + EPI_THREADS;
     // setmaxnreg pool = registers the CTA is launched with (regs/thread x THREADS, 80 x 768 or 128 x 512):
@@ -98,6 +101,15 @@ struct Cfg {
     static constexpr int EPI_REGS = (EPI_WG == 4) ? 96 : 200;
     static constexpr int EXP_REGS = (EPI_WG == 4) ? 64 : 72;
     static constexpr int CPT = M_TILE / EPI_WG;                    // columns per epilogue thread
+#ifndef FLEXQ_LOPS_BIG
+#define FLEXQ_LOPS_BIG 2
+#endif
+#ifndef FLEXQ_LOPS_SMALL
+#define FLEXQ_LOPS_SMALL 2
+#endif
+    // of every 4 accumulator elements, how many get their float bias by LOP3 (ALU pipe) instead of an
+    // integer add (FMA pipe): balances the two pipes against the expander's ALU work (measured per tile)
+    static constexpr int MAGIC_LOPS = (M_TILE >= 192) ? FLEXQ_LOPS_BIG : FLEXQ_LOPS_SMALL;
     static constexpr int CH = (EPI_WG == 4) ? 16 : (CPT < 32 ? CPT : 32);   // columns per tcgen05.ld
     static_assert(CPT % CH == 0 && (CH == 8 || CH == 16 || CH == 32), "epilogue chunking");
 };
@@ -113,6 +125,18 @@ constexpr bool kRearm = FLEXQ_REARM != 0;
 // owner(u) = the CTA whose unit range [floor(c*U/P), floor((c+1)*U/P)) contains u
 __device__ __forceinline__ int unit_owner(int u, int U, int P) {
     return (int)((((long long)u + 1) * P - 1) / U);
+}
+
+// int32 group sum 4S (|4S| <= 2^21) -> the float 12582912 + 4S, bit-wise: the low 23 bits of 4S with bit 22
+// flipped are 4S + 2^22, i.e. the mantissa of 2^23 + 2^22 + 4S.  One LOP3 on the ALU pipe; an integer add with an
+// immediate (VIADD) would share the FMA pipe with the two FFMA2 of every element pair.
+template <bool REARMED, bool LOP>
+__device__ __forceinline__ float magic_f32(uint32_t s) {
+    if (REARMED) return __uint_as_float(s);
+    if (!LOP) return __uint_as_float(s + 0x4B400000u);
+    uint32_t r;
+    asm("lop3.b32 %0, %1, 0x007fffff, 0x4b400000, 0x6a;" : "=r"(r) : "r"(s));   // (s & 0x7fffff) ^ 0x4b400000
+    return __uint_as_float(r);
 }
 
 template <int M_TILE, int GP, bool DUMP, bool TRACE>
@@ -470,10 +494,20 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             for (int q = 0; q < CH; q += 4) {
                                 const float4 s4 = *reinterpret_cast<const float4*>(sxs + c * CH + q);
                                 constexpr uint32_t kAdd = kRearm ? 0u : kMagicI;   // int32 4S -> bits of the float (kMagicF + 4S)
-                                const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 0] + kAdd), __uint_as_float(cur[q + 1] + kAdd)), sw2, bias2);
-                                const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(cur[q + 2] + kAdd), __uint_as_float(cur[q + 3] + kAdd)), sw2, bias2);
+#ifdef FLEXQ_EXP_SCALAR
+                                float2& a0 = acc[(c * CH + q) / 2];
+                                float2& a1 = acc[(c * CH + q) / 2 + 1];
+                                a0.x = fmaf(fmaf(__uint_as_float(cur[q + 0] + kAdd), sw2.x, bias2.x), s4.x, a0.x);
+                                a0.y = fmaf(fmaf(__uint_as_float(cur[q + 1] + kAdd), sw2.x, bias2.x), s4.y, a0.y);
+                                a1.x = fmaf(fmaf(__uint_as_float(cur[q + 2] + kAdd), sw2.x, bias2.x), s4.z, a1.x);
+                                a1.y = fmaf(fmaf(__uint_as_float(cur[q + 3] + kAdd), sw2.x, bias2.x), s4.w, a1.y);
+#else
+                                constexpr int L = C::MAGIC_LOPS;
+                                const float2 t0 = __ffma2_rn(make_float2(magic_f32<kRearm, (L > 0)>(cur[q + 0]), magic_f32<kRearm, (L > 2)>(cur[q + 1])), sw2, bias2);
+                                const float2 t1 = __ffma2_rn(make_float2(magic_f32<kRearm, (L > 1)>(cur[q + 2]), magic_f32<kRearm, (L > 3)>(cur[q + 3])), sw2, bias2);
                                 acc[(c * CH + q) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c * CH + q) / 2]);
                                 acc[(c * CH + q) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c * CH + q) / 2 + 1]);
+#endif
                             }
                         }
                     }
