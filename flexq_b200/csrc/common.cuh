@@ -46,6 +46,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// suspend-time hint: the hardware may park the warp for up to this long per try instead of returning
+// at once, which keeps waiting warps out of the issue slots and the FMA pipe (loop counter) of the
+// warps that do the work
+constexpr uint32_t kTryWaitHintNs = 2000;
+__device__ __forceinline__ bool mbar_try_wait_parked(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(kTryWaitHintNs)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -64,6 +79,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
+    }
+}
+// same for warps whose wake-up latency does not matter (producers running several stages ahead)
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_parked(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();          // >= 60 ms even if the hint is ignored, <= 9 s if honoured
     }
 }
 

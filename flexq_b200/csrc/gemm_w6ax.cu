@@ -227,7 +227,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 for (int g = g0; g < g1; g += GP, it++) {
                     const int ng = min(GP, g1 - g);
                     const int s = it % C::NW;
-                    mbar_wait(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
+                    mbar_wait_parked(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
                     FQ_TRACE(it, 0);
                     mbar_expect_tx(bar_w_full(s), ng * kTileBytes);
                     if (p.m_tiles == 1) {
@@ -259,7 +259,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     {   // [ng][M_TILE][128 B] swizzle-128B tiles, one TMA per k-group; rows >= M are zero-filled
                         const int ng = min(GP, g1 - g);
                         const int s = it % C::NX;
-                        if (it >= C::NX) mbar_wait(bar_done(it - C::NX), done_parity(it - C::NX));
+                        if (it >= C::NX) mbar_wait_parked(bar_done(it - C::NX), done_parity(it - C::NX));
                         FQ_TRACE(it, 9);
                         mbar_expect_tx(bar_x_full(s), ng * (M_TILE * 128));
                         for (int j = 0; j < ng; j++)
@@ -269,7 +269,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (!DUMP) {   // sx[g..g+GP][m0..] (f32) and w_scale[g..g+GP][n0..] (f16)
                         const int s = it % C::NS;
                         const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
-                        mbar_wait(bar_s_empty(s), ((it / C::NS) & 1) ^ 1);
+                        mbar_wait_parked(bar_s_empty(s), ((it / C::NS) & 1) ^ 1);
                         mbar_expect_tx(bar_s_full(s), C::S_BYTES);
                         tma_load_2d(dst, &tmap_sx, mt * M_TILE, g, bar_s_full(s));
                         tma_load_2d(dst + C::SX_BYTES, &tmap_sw, nt * kTileN, g, bar_s_full(s));
