@@ -400,6 +400,14 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         asm volatile("griddepcontrol.wait;" ::: "memory");         // D and the split-K scratch belong to earlier kernels until now
         float2 acc[CPT / 2];
         int it = 0;
+        int ss = 0, dn = 0, ab = 0;
+        uint32_t s_par = 0, dn_par = 0;
+        uint32_t s_base = smem_base + C::OFF_S;
+        asm volatile("" : "+r"(s_base));              // opaque: keep it in a register instead of re-deriving it every step
+        const uint32_t bar_s_full0 = s_base + (C::OFF_BAR - C::OFF_S) + 8u * (2 * C::NW);
+        const uint32_t bar_s_empty0 = bar_s_full0 + 8u * C::NS;
+        const uint32_t bar_acc_empty0 = bar_s_full0 + 8u * (2 * C::NS + C::NAT + C::NX);
+        const uint32_t bar_done0 = bar_acc_empty0 + 8u * C::NAB;
         for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
             for (int u = u_begin; u < u_end;) {
             const int nt = u / G, g0 = u - nt * G;
@@ -411,10 +419,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int j = 0; j < CPT / 2; j++) acc[j] = make_float2(0.f, 0.f);
             for (int g = g0; g < g1; g += GP, it++) {
                 const int ng = min(GP, g1 - g);
-                const int ab = it % C::NAB, ss = it % C::NS;
-                const uint8_t* sblk = smem + C::OFF_S + ss * C::S_BYTES;
-                if (!DUMP) mbar_wait(bar_s_full(ss), (it / C::NS) & 1);
-                mbar_wait(bar_done(it), done_parity(it));
+                // ring positions are carried, not derived from `it`: no div/mod or address rebuild per step
+                const uint32_t sblk = s_base + (uint32_t)ss * C::S_BYTES;
+                if (!DUMP) mbar_wait(bar_s_full0 + 8u * ss, s_par);
+                mbar_wait(bar_done0 + 8u * dn, dn_par);
                 if (e == 0) FQ_TRACE(it, 6);
                 tc_fence_after();
                 // TMEM drain, software pipelined: the load of chunk c+1 is in flight while chunk c is
@@ -443,7 +451,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #ifdef FLEXQ_EXP_NOEPI
                 // experiment: upper bound of the producer/expander/MMA side (no TMEM drain, results invalid)
                 tc_fence_before();
-                mbar_arrive(bar_acc_empty(ab));
+                mbar_arrive(bar_acc_empty0 + 8u * ab);
                 if (false)
 #endif
                 ld_chunk(0, 0, v[0]);
@@ -454,9 +462,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     break;
 #endif
                     float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
-                    const float* sxs = reinterpret_cast<const float*>(sblk) + j * M_TILE + col0;
+                    const uint32_t sxs = sblk + (uint32_t)(j * M_TILE + col0) * 4u;
                     if (!DUMP) {
-                        const float swv = n_ok ? 0.25f * __half2float(reinterpret_cast<const __half*>(sblk + C::SX_BYTES)[j * kTileN + r]) : 0.f;   // operands hold 4*w
+                        const float swv = n_ok ? 0.25f * __half2float(__ushort_as_half(lds_u16(sblk + C::SX_BYTES + (uint32_t)(j * kTileN + r) * 2u))) : 0.f;   // operands hold 4*w
                         sw2 = make_float2(swv, swv);
                         bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
                     }
@@ -475,7 +483,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         } else {
                             if constexpr (kRearm) tmem_wait_st();    // every chunk read (and re-armed):
                             tc_fence_before();                       // hand the buffer back before the last math
-                            mbar_arrive(bar_acc_empty(ab));
+                            mbar_arrive(bar_acc_empty0 + 8u * ab);
                         }
                         if constexpr (DUMP) {
                             if (n_ok) {
@@ -492,7 +500,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #endif
 #pragma unroll
                             for (int q = 0; q < CH; q += 4) {
-                                const float4 s4 = *reinterpret_cast<const float4*>(sxs + c * CH + q);
+                                const float4 s4 = lds_f4(sxs + (uint32_t)(c * CH + q) * 4u);
                                 constexpr uint32_t kAdd = kRearm ? 0u : kMagicI;   // int32 4S -> bits of the float (kMagicF + 4S)
 #ifdef FLEXQ_EXP_SCALAR
                                 float2& a0 = acc[(c * CH + q) / 2];
@@ -513,7 +521,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                 }
                 if (e == 0) FQ_TRACE(it, 7);
-                if (!DUMP) mbar_arrive(bar_s_empty(ss));
+                if (!DUMP) mbar_arrive(bar_s_empty0 + 8u * ss);
+                if (++ss == C::NS) { ss = 0; s_par ^= 1u; }
+                if (++dn == C::NDONE) { dn = 0; dn_par ^= 1u; }
+                ab = (ab + 1 == C::NAB) ? 0 : ab + 1;
             }
             if (e == 0) FQ_TRACE(it - 1, 10);
             if constexpr (!DUMP) {
