@@ -88,9 +88,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // hanging the GPU.  No printf here: a call inside the spin loop would force every live register
 // of the caller to be spilled around it.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    // register-register add (IADD3, ALU pipe): an add with an immediate becomes VIADD on the FMA pipe,
+    // where a spinning warp would take cycles from the epilogue's FFMA2
+    uint32_t spins = 0, one = 1;
+    asm volatile("" : "+r"(one));
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        spins += one;
+        if (spins > (1u << 26)) __trap();
     }
 }
 // same for warps whose wake-up latency does not matter (producers running several stages ahead)
