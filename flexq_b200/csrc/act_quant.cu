@@ -67,32 +67,110 @@ __device__ __forceinline__ float quant8(const uint4& raw, int bits, int* q) {
     return r;
 }
 
-template <int MODE>
+// Fast path of the CUDA-mode quantiser for one thread's 8 halves -> 8 int8 containers in two words.
+// Same integers as quant8<FLEXQ_ROUND_CUDA> (the reference's round-half-away of the IEEE quotient,
+// bit_packing.cu:151-160) or `fallback` is set and the caller recomputes with the exact routine:
+//   * t = |x| * rcp(r) is within 2 ulp of |x| / r (<= 1 unit of 2^-16 for t < 128);
+//   * a = t + 128.5 + 4*2^-16, rounded down, lies in [128, 256) where one ulp is 2^-16: byte 2 of its
+//     bit pattern is floor(t + 0.5) and the low 16 bits are the fraction, shifted by 4 units;
+//   * the integer can only differ from the exact one when that fraction is within [0, 16) -- then fall back;
+//   * signs come back with one PRMT (sign replication) and a per-byte negate without cross-byte carries.
+// Anything unusual (r == 0, denormal/inf/NaN scale, a NaN input, t that could reach hi + 0.5) also falls back.
+__device__ __forceinline__ float quant8_fast(const uint4& raw, int bits, uint2& packed, bool& fallback) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t aw[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) aw[i] = w[i] & 0x7FFF7FFFu;
+    // |x| max; the NaN-propagating forms make a NaN input poison amax (-> fallback)
+    const __half2 m2 = __hmax2_nan(__hmax2_nan(*reinterpret_cast<__half2*>(&aw[0]), *reinterpret_cast<__half2*>(&aw[1])),
+                                   __hmax2_nan(*reinterpret_cast<__half2*>(&aw[2]), *reinterpret_cast<__half2*>(&aw[3])));
+    uint32_t ab = __float_as_uint(__half2float(__hmax_nan(__low2half(m2), __high2half(m2))));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ab = max(ab, __shfl_xor_sync(0xffffffffu, ab, o));   // non-negative floats order like integers, NaN on top
+    const float amax = __uint_as_float(ab);
+    const float hi = (float)((1 << (bits - 1)) - 1);
+    // r = half(amax / hi).  amax is a half (11-bit significand n) and hi is odd (31 / 127), so n / hi is either
+    // exactly representable or at least 2^-19 (relative) away from every half rounding boundary; the product
+    // with the rounded reciprocal is within 2^-23 of it and therefore rounds to the same half.
+    const float r = __half2float(__float2half_rn(amax * (bits == 6 ? 1.f / 31.f : 1.f / 127.f)));
+    float rcp;                                                            // <= 1 ulp off 1/r: part of the 2-ulp budget above
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(r));
+    fallback = !(r > 0.f && rcp < 3.0e38f && amax * rcp < hi + 0.49f);    // false for NaN amax as well
+    const float2 rcp2 = make_float2(rcp, rcp);
+    constexpr float kBias = 128.5f + 4.f / 65536.f;
+    uint32_t b[8];
+    uint32_t tie = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __half22float2(*reinterpret_cast<__half2*>(&aw[i]));
+        const float2 t = __fmul2_rn(f, rcp2);
+        b[2 * i] = __float_as_uint(__fadd_rd(t.x, kBias));
+        b[2 * i + 1] = __float_as_uint(__fadd_rd(t.y, kBias));
+        tie = min(tie, min(b[2 * i] & 0xFFF0u, b[2 * i + 1] & 0xFFF0u));
+    }
+    fallback |= tie == 0u;
+    constexpr uint32_t H = 0x80808080u;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t m01 = __byte_perm(b[4 * j], b[4 * j + 1], 0x0062);
+        const uint32_t m23 = __byte_perm(b[4 * j + 2], b[4 * j + 3], 0x0062);
+        const uint32_t mag = __byte_perm(m01, m23, 0x5410);                    // 4 magnitudes, each <= 127
+        uint32_t sg;                                                           // 0xFF where the half is negative:
+        asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(sg) : "r"(w[2 * j]), "r"(w[2 * j + 1]));   // selector msb = replicate the byte's sign
+        const uint32_t q = (((mag ^ sg) | H) - (sg & ~H)) ^ H;                 // per byte: sg ? -mag : mag
+        if (j == 0) packed.x = q; else packed.y = q;
+    }
+    return r;
+}
+
+// grid = (rows of sx incl. padding, column blocks).  A warp owns U consecutive pairs of groups of one
+// token row (32 lanes x 8 halves = 2 groups per pass); all U loads are issued before the arithmetic.
+template <int MODE, int U>
 __global__ void __launch_bounds__(256) quant_act_native_kernel(const uint4* __restrict__ x, int8_t* __restrict__ xq,
                                                                float* __restrict__ sx, int M, int K, int ldsx, int bits) {
     // programmatic dependent launch: the GEMM that consumes Xq/sx may start streaming its weights now;
     // this kernel itself waits for the producer of X (no-ops when launched without the attribute)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int G = K / kGroup;
-    const long long vec = (long long)blockIdx.x * blockDim.x + threadIdx.x;    // 8-half vector index
-    const long long grp = vec >> 4;                                           // (row, group) index
+    const int m = blockIdx.x;
     const int lane16 = threadIdx.x & 15;
-    const long long total = (long long)ldsx * G;
-    if (grp >= total) return;                      // whole 16-lane groups exit together
-    const int m = (int)(grp / G), g = (int)(grp - (long long)m * G);
+    const int nvec = K >> 3;                                                // 8-half vectors per row
+    const int v0 = ((blockIdx.y * 8 + (threadIdx.x >> 5)) * U) * 32 + (threadIdx.x & 31);
     if (m >= M) {                                  // padding rows of sx
-        if (lane16 == 0) sx[(size_t)g * ldsx + m] = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int v = v0 + u * 32;
+            if (v < nvec && lane16 == 0) sx[(size_t)(v >> 4) * ldsx + m] = 0.f;
+        }
         return;
     }
-    const uint4 raw = __ldg(x + ((size_t)m * K + (size_t)g * kGroup) / 8 + lane16);
-    int q[8];
-    const float r = quant8<MODE>(raw, bits, q);
-    uint2 o;
-    o.x = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
-    o.y = (uint32_t)(q[4] & 0xFF) | ((uint32_t)(q[5] & 0xFF) << 8) | ((uint32_t)(q[6] & 0xFF) << 16) | ((uint32_t)(q[7] & 0xFF) << 24);
-    *reinterpret_cast<uint2*>(xq + (size_t)m * K + (size_t)g * kGroup + lane16 * 8) = o;
-    if (lane16 == 0) sx[(size_t)g * ldsx + m] = r;
+    const uint4* xrow = x + (size_t)m * nvec;
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int v = v0 + u * 32;
+        raw[u] = v < nvec ? __ldg(xrow + v) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int v = v0 + u * 32;
+        if (v >= nvec) break;                      // whole 16-lane groups leave together (nvec % 16 == 0)
+        uint2 o;
+        float r;
+        bool slow = true;
+        if (MODE == FLEXQ_ROUND_CUDA) {
+            r = quant8_fast(raw[u], bits, o, slow);
+            slow = __any_sync(__activemask(), slow);       // the exact routine shuffles across the group's 16 lanes
+        }
+        if (slow) {
+            int q[8];
+            r = quant8<MODE>(raw[u], bits, q);
+            o.x = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+            o.y = (uint32_t)(q[4] & 0xFF) | ((uint32_t)(q[5] & 0xFF) << 8) | ((uint32_t)(q[6] & 0xFF) << 16) | ((uint32_t)(q[7] & 0xFF) << 24);
+        }
+        *reinterpret_cast<uint2*>(xq + (size_t)m * K + (size_t)v * 8) = o;
+        if (lane16 == 0) sx[(size_t)(v >> 4) * ldsx + m] = r;
+    }
 }
 
 // Reference plane layout.  Lane l (0..15) of a group owns k = 8l..8l+7; plane word k32 = l/4 is
@@ -134,10 +212,12 @@ int quant_act_native(const __half* x, int8_t* xq, float* sx, int M, int K, int b
     if (M <= 0 || K < kGroup || K % kGroup) return FLEXQ_ERR_BAD_SHAPE;
     if (bits != 6 && bits != 8) return FLEXQ_ERR_BAD_BITS;
     const int ldsx = ceil4(M);
-    const long long threads = (long long)ldsx * (K / kGroup) * 16;
-    const int blocks = (int)((threads + 255) / 256);
+    const int nvec = K / 8;
+    // 4 vectors per thread once there is enough work to fill the machine; 1 for decode-sized inputs (latency)
+    const bool big = (long long)ldsx * nvec >= 4LL * 148 * 2048;
+    const int per_block = 256 * (big ? 4 : 1);
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(blocks);
+    cfg.gridDim = dim3(ldsx, (nvec + per_block - 1) / per_block);
     cfg.blockDim = dim3(256);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -146,8 +226,12 @@ int quant_act_native(const __half* x, int8_t* xq, float* sx, int M, int K, int b
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint4* xv = reinterpret_cast<const uint4*>(x);
-    if (mode == FLEXQ_ROUND_PYTHON) return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_PYTHON>, xv, xq, sx, M, K, ldsx, bits);
-    return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_CUDA>, xv, xq, sx, M, K, ldsx, bits);
+    if (mode == FLEXQ_ROUND_PYTHON) {
+        if (big) return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_PYTHON, 4>, xv, xq, sx, M, K, ldsx, bits);
+        return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_PYTHON, 1>, xv, xq, sx, M, K, ldsx, bits);
+    }
+    if (big) return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_CUDA, 4>, xv, xq, sx, M, K, ldsx, bits);
+    return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_CUDA, 1>, xv, xq, sx, M, K, ldsx, bits);
 }
 
 int quant_act_planes(const __half* x, uint32_t* planes, __half* xs, int M, int K, int bits, cudaStream_t stream) {

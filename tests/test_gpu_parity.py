@@ -103,6 +103,41 @@ def test_quant_act_cuda_mode(capi, oracle, M, K, bits):
     assert np.all(sx[:, M:] == 0)
 
 
+@pytest.mark.parametrize("bits", [6, 8])
+def test_quant_act_cuda_mode_stress(capi, oracle, bits):
+    """Rounding corner cases of the fast path: exact .5 ties of either sign, values a hair beside a tie,
+    every magnitude range of the scale (normal, half-denormal, huge), signed zeros and infinities."""
+    rng = np.random.default_rng(100 + bits)
+    M, K = 768, 2048
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    x *= (10.0 ** rng.uniform(-7.5, 4.0, size=(M, 1))).astype(np.float32)          # row magnitudes 3e-8 .. 1e4
+    x = x.astype(np.float16)
+    hi = (1 << (bits - 1)) - 1
+    # rows whose scale is a power of two: (k + 0.5) * r and its neighbours are exact halves
+    for row, e in zip(range(0, 64), np.linspace(-14, 6, 64).astype(int)):
+        r = np.float32(2.0) ** e
+        k = rng.integers(-hi, hi, size=K).astype(np.float32)
+        v = (k + np.float32(0.5)) * r
+        v[::128] = hi * r                                                              # pins absmax/hi == r in every group
+        h = v.astype(np.float16)
+        nudge = rng.integers(-1, 2, size=K)                                            # -1, 0, +1 ulp beside the tie
+        h = (h.view(np.int16) + nudge.astype(np.int16)).view(np.float16)
+        h[::128] = np.float16(hi * r)
+        x[row] = h
+    x[64, :256] = 0
+    x[65, :128] = np.float16(-0.0)
+    x[66, 7] = np.float16(np.inf)
+    x[67, 300] = np.float16(-np.inf)
+    x[68, :128] = np.float16(6e-8)                                                     # smallest half denormal
+    x[69, :] = np.float16(65504.0) * np.sign(rng.standard_normal(K)).astype(np.float16)
+    q_ref, s_ref = oracle.quant_act_cuda(x, bits)
+    xq, sx = capi.quant_act(torch.from_numpy(x).cuda(), bits, capi.ROUND_CUDA)
+    got = xq.cpu().numpy().astype(np.int32)
+    bad = np.argwhere(got != q_ref)
+    assert bad.size == 0, (bad[:5], got[tuple(bad[0])], q_ref[tuple(bad[0])], x[tuple(bad[0])])
+    assert np.array_equal(sx.cpu().numpy()[:, :M].T.view(np.uint32), s_ref.astype(np.float32).view(np.uint32))
+
+
 @pytest.mark.parametrize("M,K,bits", [(5, 384, 6), (16, 1024, 8)])
 def test_quant_act_python_mode(capi, oracle, M, K, bits):
     x = _act_inputs(np.random.default_rng(M + bits), M, K)
