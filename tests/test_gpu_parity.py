@@ -331,3 +331,25 @@ def test_quantlinear_module_vs_reference_golden(capi, case):
     # 3-D input [1, S, K] as the reference's decoder layers pass it (quantizer.py:100-103)
     y3 = ql(torch.from_numpy(x).cuda().unsqueeze(0))
     assert y3.shape == (1, x.shape[0], w.shape[0]) and torch.equal(y3[0], y)
+
+
+def test_host_staged_pipeline_matches_direct_call(capi):
+    """Host-buffer front end (three-stream pipeline) returns what the direct device call does,
+    pass after pass (staging buffers are reused)."""
+    from flexq_b200 import tp
+    from flexq_b200.host_io import HostStagedLinears
+    dev = torch.device("cuda")
+    torch.manual_seed(5)
+    layers, M = [], 96
+    for N, K, xb in [(256, 512, 6), (384, 256, 8), (128, 1024, 6)]:
+        w6, wsc = capi.quant_pack_w6((0.05 * torch.randn(N, K, device=dev)).half())
+        layers.append(tp.TPLinearW6Ax.from_packed(w6, wsc, N, K, "column", xb, 0, 1))
+    pipe = HostStagedLinears(layers, M, dev)
+    for it in range(3):
+        xs = [torch.randn(M - it, l.K).half().pin_memory() for l in layers]
+        ys = [torch.empty(M - it, l.N, dtype=torch.float16).pin_memory() for l in layers]
+        pipe.run(xs, ys)
+        pipe.synchronize()
+        for l, xh, yh in zip(layers, xs, ys):
+            # split-K partial sums meet in fp32 atomics whose order is not fixed: equal up to an fp16 rounding
+            assert torch.allclose(l.forward(xh.cuda()).cpu().float(), yh.float(), rtol=2e-3, atol=2e-3)
