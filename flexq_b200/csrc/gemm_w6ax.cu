@@ -91,15 +91,15 @@ struct Cfg {
     // prefill throughput as 2 (8 warps, 200 regs) -- the epilogue is bound by issue slots / FMA-heavy
     // pipe, not by latency hiding -- so the simpler 512-thread shape is used everywhere.
 #ifndef FLEXQ_EPI_WG
-#define FLEXQ_EPI_WG 2
+#define FLEXQ_EPI_WG 3
 #endif
-    static constexpr int EPI_WG = (FLEXQ_EPI_WG == 4 && M_TILE >= 128) ? 4 : 2;
+    static constexpr int EPI_WG = (FLEXQ_EPI_WG == 4 && M_TILE >= 128) ? 4 : (FLEXQ_EPI_WG == 3 && M_TILE == 192) ? 3 : 2;
     static constexpr int EPI_THREADS = 128 * EPI_WG;
     static constexpr int THREADS = 256 + EPI_THREADS;
-    // setmaxnreg pool = registers the CTA is launched with (regs/thread x THREADS, 80 x 768 or 128 x 512):
-    //   768 threads: 128*32 + 128*64 + 512*96  = 61440;   512 threads: 128*32 + 128*72 + 256*200 = 64512
-    static constexpr int EPI_REGS = (EPI_WG == 4) ? 96 : 200;
-    static constexpr int EXP_REGS = (EPI_WG == 4) ? 64 : 72;
+    // setmaxnreg pool = registers the CTA is launched with (regs/thread x THREADS: 80 x 768, 96 x 640 or 128 x 512):
+    //   768 threads: 128*32 + 128*64 + 512*96 = 61440;  640: 128*32 + 128*64 + 384*128 = 61440;  512: 128*32 + 128*72 + 256*200 = 64512
+    static constexpr int EPI_REGS = (EPI_WG == 4) ? 96 : (EPI_WG == 3) ? 128 : 200;
+    static constexpr int EXP_REGS = (EPI_WG >= 3) ? 64 : 72;
     static constexpr int CPT = M_TILE / EPI_WG;                    // columns per epilogue thread
 #ifndef FLEXQ_LOPS_BIG
 #define FLEXQ_LOPS_BIG 2
@@ -110,7 +110,7 @@ struct Cfg {
     // of every 4 accumulator elements, how many get their float bias by LOP3 (ALU pipe) instead of an
     // integer add (FMA pipe): balances the two pipes against the expander's ALU work (measured per tile)
     static constexpr int MAGIC_LOPS = (M_TILE >= 192) ? FLEXQ_LOPS_BIG : FLEXQ_LOPS_SMALL;
-    static constexpr int CH = (EPI_WG == 4) ? 16 : (CPT < 32 ? CPT : 32);   // columns per tcgen05.ld
+    static constexpr int CH = (EPI_WG >= 3) ? 16 : (CPT < 32 ? CPT : 32);   // columns per tcgen05.ld
     static_assert(CPT % CH == 0 && (CH == 8 || CH == 16 || CH == 32), "epilogue chunking");
 };
 
