@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libflexq_b200.so")
-SOURCES = ["capi.cu", "act_quant.cu", "weight_pack.cu", "planes.cu", "gemm_w6ax.cu"]
+SOURCES = ["capi.cu", "act_quant.cu", "weight_pack.cu", "planes.cu", "gemm_w6ax.cu", "allreduce.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "flexq_b200.h")]
 EXTRA = os.environ.get("FLEXQ_NVCC_EXTRA", "").split()
 NVCC_FLAGS = [*EXTRA, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

@@ -47,6 +47,9 @@ _SIGNATURES = {
     "flexq_debug_gemm_trace": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "flexq_linear_w6ax_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_gemm_ref_layout": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "flexq_rmsnorm_quant_f16": (_i, [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "flexq_silu_mul_quant_f16": (_i, [_vp, _vp, ctypes.c_longlong, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "flexq_allreduce_sum_f16": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), _sz, _sz, _i, _i, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -123,6 +126,36 @@ def quant_act(x: torch.Tensor, bits: int, mode: int = ROUND_CUDA):
     sx = torch.empty(K // GROUP, ceil4(M), dtype=torch.float32, device=x.device)
     check(load().flexq_quant_act(_ptr(x), _ptr(xq), _ptr(sx), M, K, bits, mode, _stream()), "flexq_quant_act")
     return xq, sx
+
+
+def rmsnorm_quant(x: torch.Tensor, gamma: torch.Tensor, eps: float, bits: int, residual: torch.Tensor | None = None,
+                  want_normed: bool = False):
+    """Fused (residual add +) RMSNorm + activation quantise.  `residual` is updated in place to x + residual.
+    Returns (xq, sx, normed or None)."""
+    M, K = x.shape
+    xq = torch.empty(M, K, dtype=torch.int8, device=x.device)
+    sx = torch.empty(K // GROUP, ceil4(M), dtype=torch.float32, device=x.device)
+    normed = torch.empty_like(x) if want_normed else None
+    check(load().flexq_rmsnorm_quant_f16(_ptr(x), _ptr(residual) if residual is not None else None, _ptr(gamma), float(eps),
+                                         _ptr(normed) if normed is not None else None, _ptr(xq), _ptr(sx), M, K, bits, _stream()),
+          "flexq_rmsnorm_quant_f16")
+    return xq, sx, normed
+
+
+def silu_mul_quant(gate: torch.Tensor, up: torch.Tensor, bits: int = 8, want_out: bool = False):
+    """Fused SiLU(gate) * up + activation quantise.  gate/up: [M, K] fp16 views with equal row stride
+    (e.g. the two halves of a fused gate_up output).  Returns (xq, sx, out or None)."""
+    M, K = gate.shape
+    if gate.stride(1) != 1 or up.stride(1) != 1 or gate.stride(0) != up.stride(0):
+        raise FlexQError("silu_mul_quant: gate/up must be row-major with the same row stride")
+    xq = torch.empty(M, K, dtype=torch.int8, device=gate.device)
+    sx = torch.empty(K // GROUP, ceil4(M), dtype=torch.float32, device=gate.device)
+    out = torch.empty(M, K, dtype=torch.float16, device=gate.device) if want_out else None
+    gp, up_ = ctypes.c_void_p(gate.data_ptr()), ctypes.c_void_p(up.data_ptr())      # strided views: pass raw pointers
+    assert gate.is_cuda and up.is_cuda and gate.dtype == torch.float16 and up.dtype == torch.float16
+    check(load().flexq_silu_mul_quant_f16(gp, up_, gate.stride(0), _ptr(out) if out is not None else None,
+                                          _ptr(xq), _ptr(sx), M, K, bits, _stream()), "flexq_silu_mul_quant_f16")
+    return xq, sx, out
 
 
 def _new_w6(N, K, device):
@@ -202,3 +235,11 @@ def gemm_ref_layout(x_planes, x_scale, w6, w_scale, M: int, N: int, K: int, x_bi
     check(load().flexq_gemm_ref_layout(_ptr(x_planes), _ptr(x_scale), _ptr(w6), _ptr(w_scale), _ptr(out), M, N, K, x_bits,
                                        _ptr(workspace), workspace.numel(), _stream()), "flexq_gemm_ref_layout")
     return out
+
+
+def allreduce_sum_f16(multicast_ptr: int, peer_ptrs, offset_elems: int, elems: int, rank: int, world: int):
+    """In-place sum of a symmetric-memory fp16 buffer over `world` ranks (this rank's slice; see the header).
+    `multicast_ptr` 0/None selects the peer-pointer path."""
+    arr = (ctypes.c_void_p * 8)(*([int(p) for p in peer_ptrs] + [0] * (8 - len(peer_ptrs)))) if peer_ptrs else None
+    check(load().flexq_allreduce_sum_f16(ctypes.c_void_p(int(multicast_ptr or 0)), arr, offset_elems, elems, rank, world, _stream()),
+          "flexq_allreduce_sum_f16")

@@ -173,6 +173,214 @@ __global__ void __launch_bounds__(256) quant_act_native_kernel(const uint4* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Producer-side fusions: the op that produces a GEMM's activations quantises them in
+// the same pass, so the fp16 tensor makes no HBM round trip between the producer and the quantiser.
+// Both kernels end in the same per-thread quantiser as quant_act_native_kernel (identical integers and
+// scales for identical fp16 values).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clamp_half_range(float v) {      // clamp_inf_for_half<half>, reduce_kernel_utils.cuh:356-361
+    return v > 0.f ? fminf(v, 65504.f - 1000.f) : fmaxf(v, -65504.f + 1000.f);
+}
+
+template <int MODE>
+__device__ __forceinline__ void quant_store(const uint4& raw, int m, int v, int K, int ldsx, int bits, int8_t* __restrict__ xq,
+                                            float* __restrict__ sx, int lane16) {
+    uint2 o;
+    float r;
+    bool slow = true;
+    if (MODE == FLEXQ_ROUND_CUDA) {
+        r = quant8_fast(raw, bits, o, slow);
+        slow = __any_sync(__activemask(), slow);
+    }
+    if (slow) {
+        int q[8];
+        r = quant8<MODE>(raw, bits, q);
+        o.x = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+        o.y = (uint32_t)(q[4] & 0xFF) | ((uint32_t)(q[5] & 0xFF) << 8) | ((uint32_t)(q[6] & 0xFF) << 16) | ((uint32_t)(q[7] & 0xFF) << 24);
+    }
+    *reinterpret_cast<uint2*>(xq + (size_t)m * K + (size_t)v * 8) = o;
+    if (lane16 == 0) sx[(size_t)(v >> 4) * ldsx + m] = r;
+}
+
+// RMSNorm (T5 style: no mean, no bias) with optional residual add, then quantise.  One CTA per token row,
+// the row stays in registers between the two passes.  Arithmetic of the reference kernels
+// generalT5LayerNormFlexQFusion / generalAddResidualT5LayerNormFlexQFusion (layernorm_kernels.cu:2494-2517,
+// 1852-1905): residual' = half(clamp(x + residual)); var = sum(h^2) / K in fp32; rstd = rsqrtf(var + eps);
+// y = half(clamp((float(h) * rstd) * float(gamma))); then the a6 quantiser on y.
+template <int U, bool RESID>
+__global__ void __launch_bounds__(256) rmsnorm_quant_kernel(const uint4* __restrict__ x, uint4* __restrict__ resid,
+                                                            const uint4* __restrict__ gamma, uint4* __restrict__ normed,
+                                                            int8_t* __restrict__ xq, float* __restrict__ sx, float eps, int M, int K,
+                                                            int ldsx, int bits) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int m = blockIdx.x;
+    const int lane16 = threadIdx.x & 15;
+    const int nvec = K >> 3;
+    if (m >= M) {
+        for (int v = threadIdx.x; v < nvec; v += 256)
+            if ((v & 15) == 0) sx[(size_t)(v >> 4) * ldsx + m] = 0.f;
+        return;
+    }
+    uint4 raw[U];
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int v = u * 256 + threadIdx.x;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (v < nvec) {
+            raw[u] = __ldg(x + (size_t)m * nvec + v);
+            if (RESID) {
+                const uint4 rr = resid[(size_t)m * nvec + v];
+                __half2* a = reinterpret_cast<__half2*>(&raw[u]);
+                const __half2* b = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 fa = __half22float2(a[i]), fb = __half22float2(b[i]);
+                    a[i] = __floats2half2_rn(clamp_half_range(fa.x + fb.x), clamp_half_range(fa.y + fb.y));
+                }
+                resid[(size_t)m * nvec + v] = raw[u];
+            }
+            const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float2 f = __half22float2(h[i]);
+                ss = fmaf(f.x, f.x, ss);
+                ss = fmaf(f.y, f.y, ss);
+            }
+        }
+    }
+    __shared__ float warp_sum[8];
+    __shared__ float s_rstd;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += warp_sum[w];
+        s_rstd = rsqrtf(t / (float)K + eps);
+    }
+    __syncthreads();
+    const float rstd = s_rstd;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int v = u * 256 + threadIdx.x;
+        if (v >= nvec) break;
+        const uint4 gg = __ldg(gamma + v);
+        __half2* h = reinterpret_cast<__half2*>(&raw[u]);
+        const __half2* g2 = reinterpret_cast<const __half2*>(&gg);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 f = __half22float2(h[i]), g = __half22float2(g2[i]);
+            h[i] = __floats2half2_rn(clamp_half_range((f.x * rstd) * g.x), clamp_half_range((f.y * rstd) * g.y));
+        }
+        if (normed) normed[(size_t)m * nvec + v] = raw[u];
+        quant_store<FLEXQ_ROUND_CUDA>(raw[u], m, v, K, ldsx, bits, xq, sx, lane16);
+    }
+}
+
+// SiLU(gate) * up, then quantise (the activations of down_proj).  Arithmetic of flexq_generic_activation with
+// SiluActivation<half2> (activation_kernels.cu:129-144,246-298): silu in fp32 with __expf, product in fp32,
+// rounded once to half.  `ld_in` = row stride of gate/up in halves (2*K when they are the two halves of a fused
+// gate_up GEMM output).
+template <int U>
+__global__ void __launch_bounds__(256) silu_mul_quant_kernel(const __half* __restrict__ gate, const __half* __restrict__ up, long long ld_in,
+                                                             uint4* __restrict__ out, int8_t* __restrict__ xq, float* __restrict__ sx,
+                                                             int M, int K, int ldsx, int bits) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int m = blockIdx.x;
+    const int lane16 = threadIdx.x & 15;
+    const int nvec = K >> 3;
+    const int v0 = ((blockIdx.y * 8 + (threadIdx.x >> 5)) * U) * 32 + (threadIdx.x & 31);
+    if (m >= M) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int v = v0 + u * 32;
+            if (v < nvec && lane16 == 0) sx[(size_t)(v >> 4) * ldsx + m] = 0.f;
+        }
+        return;
+    }
+    const uint4* grow = reinterpret_cast<const uint4*>(gate + (size_t)m * ld_in);
+    const uint4* urow = reinterpret_cast<const uint4*>(up + (size_t)m * ld_in);
+    uint4 g[U], w[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int v = v0 + u * 32;
+        g[u] = v < nvec ? __ldg(grow + v) : make_uint4(0, 0, 0, 0);
+        w[u] = v < nvec ? __ldg(urow + v) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int v = v0 + u * 32;
+        if (v >= nvec) break;
+        __half2* a = reinterpret_cast<__half2*>(&g[u]);
+        const __half2* b = reinterpret_cast<const __half2*>(&w[u]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 fa = __half22float2(a[i]), fb = __half22float2(b[i]);
+            const float sx_ = __fdividef(fa.x, 1.0f + __expf(-fa.x)), sy_ = __fdividef(fa.y, 1.0f + __expf(-fa.y));
+            a[i] = __floats2half2_rn(sx_ * fb.x, sy_ * fb.y);
+        }
+        if (out) out[(size_t)m * nvec + v] = g[u];
+        quant_store<FLEXQ_ROUND_CUDA>(g[u], m, v, K, ldsx, bits, xq, sx, lane16);
+    }
+}
+
+template <typename Kern, typename... Args>
+static int launch_pdl(Kern kern, dim3 grid, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+int rmsnorm_quant(const __half* x, __half* residual, const __half* gamma, float eps, __half* normed, int8_t* xq, float* sx, int M, int K,
+                  int bits, cudaStream_t stream) {
+    if (!x || !gamma || !xq || !sx) return FLEXQ_ERR_NULL;
+    if (M <= 0 || K < kGroup || K % kGroup || K > 256 * 8 * 8) return FLEXQ_ERR_BAD_SHAPE;
+    if (bits != 6 && bits != 8) return FLEXQ_ERR_BAD_BITS;
+    const int ldsx = ceil4(M);
+    const int need = (K / 8 + 255) / 256;
+    const dim3 grid(ldsx);
+    const uint4* xv = reinterpret_cast<const uint4*>(x);
+    uint4* rv = reinterpret_cast<uint4*>(residual);
+    const uint4* gv = reinterpret_cast<const uint4*>(gamma);
+    uint4* nv = reinterpret_cast<uint4*>(normed);
+#define FQ_RMS(U_)                                                                                                              \
+    return residual ? launch_pdl(rmsnorm_quant_kernel<U_, true>, grid, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits) \
+                    : launch_pdl(rmsnorm_quant_kernel<U_, false>, grid, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits)
+    if (need <= 1) { FQ_RMS(1); }
+    if (need <= 2) { FQ_RMS(2); }
+    if (need <= 4) { FQ_RMS(4); }
+    FQ_RMS(8);
+#undef FQ_RMS
+}
+
+int silu_mul_quant(const __half* gate, const __half* up, long long ld_in, __half* out, int8_t* xq, float* sx, int M, int K, int bits,
+                   cudaStream_t stream) {
+    if (!gate || !up || !xq || !sx) return FLEXQ_ERR_NULL;
+    if (M <= 0 || K < kGroup || K % kGroup || ld_in < K || ld_in % 8) return FLEXQ_ERR_BAD_SHAPE;
+    if (bits != 6 && bits != 8) return FLEXQ_ERR_BAD_BITS;
+    const int ldsx = ceil4(M);
+    const int nvec = K / 8;
+    const bool big = (long long)ldsx * nvec >= 4LL * 148 * 2048;
+    const int per_block = 256 * (big ? 2 : 1);
+    const dim3 grid(ldsx, (nvec + per_block - 1) / per_block);
+    uint4* ov = reinterpret_cast<uint4*>(out);
+    if (big) return launch_pdl(silu_mul_quant_kernel<2>, grid, stream, gate, up, ld_in, ov, xq, sx, M, K, ldsx, bits);
+    return launch_pdl(silu_mul_quant_kernel<1>, grid, stream, gate, up, ld_in, ov, xq, sx, M, K, ldsx, bits);
+}
+
 // Reference plane layout.  Lane l (0..15) of a group owns k = 8l..8l+7; plane word k32 = l/4 is
 // assembled from the four lanes l = 4*k32 .. 4*k32+3; element k%32==0 sits in bit 31
 // (engine/src/pack/bit_packing.cu:75 "__brev(__ballot_sync)").

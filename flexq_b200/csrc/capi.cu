@@ -13,6 +13,9 @@ int planes_to_i8(const uint32_t*, int8_t*, int, int, int, cudaStream_t);
 int xscale_ref_to_sx(const __half*, float*, int, int, cudaStream_t);
 int gemm_w6ax(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, size_t, cudaStream_t);
 int gemm_w6ax_groupsums(const int8_t*, const uint8_t*, int32_t*, int, int, int, cudaStream_t);
+int rmsnorm_quant(const __half*, __half*, const __half*, float, __half*, int8_t*, float*, int, int, int, cudaStream_t);
+int silu_mul_quant(const __half*, const __half*, long long, __half*, int8_t*, float*, int, int, int, cudaStream_t);
+int allreduce_sum_f16(void*, void* const*, size_t, size_t, int, int, cudaStream_t);
 int gemm_w6ax_trace(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, long long*, int, cudaStream_t);
 }  // namespace flexq
 
@@ -127,6 +130,21 @@ int flexq_gemm_ref_layout(const int32_t* x_planes, const void* x_scale, const ui
     if (int e = planes_to_i8(reinterpret_cast<const uint32_t*>(x_planes), xq, M, K, x_bits, (cudaStream_t)stream)) return e;
     if (int e = xscale_ref_to_sx((const __half*)x_scale, sx, M, K, (cudaStream_t)stream)) return e;
     return gemm_w6ax(xq, sx, w6, (const __half*)w_scale, (__half*)d, M, N, K, ws, flexq_gemm_workspace_bytes(), (cudaStream_t)stream);
+}
+
+int flexq_rmsnorm_quant_f16(const void* x, void* residual, const void* gamma, float eps, void* normed, int8_t* xq, float* sx, int M,
+                            int K, int bits, void* stream) {
+    return rmsnorm_quant((const __half*)x, (__half*)residual, (const __half*)gamma, eps, (__half*)normed, xq, sx, M, K, bits,
+                         (cudaStream_t)stream);
+}
+int flexq_silu_mul_quant_f16(const void* gate, const void* up, long long ld_in, void* out, int8_t* xq, float* sx, int M, int K,
+                             int bits, void* stream) {
+    return silu_mul_quant((const __half*)gate, (const __half*)up, ld_in, (__half*)out, xq, sx, M, K, bits, (cudaStream_t)stream);
+}
+
+int flexq_allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset_elems, size_t elems, int rank, int world,
+                            void* stream) {
+    return allreduce_sum_f16(multicast_ptr, peer_ptrs, offset_elems, elems, rank, world, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -55,6 +55,34 @@ def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+class PeerAllReduce:
+    """fp16 sum all-reduce in a symmetric-memory buffer, done by flexq_allreduce_sum_f16 over NVLink /
+    NVSwitch peer memory (multimem in-switch reduction when the allocation has a multicast mapping).
+
+    torch.distributed._symmetric_memory is the plumbing only: it allocates the buffer, exchanges the
+    handles and provides the cross-rank stream barrier; the reduction itself is our kernel.
+    """
+
+    def __init__(self, max_elems: int, device: torch.device, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.buf = symm.empty(max_elems, dtype=torch.float16, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.multicast_ptr = mc if use_multicast else 0
+
+    def view(self, M: int, N: int) -> torch.Tensor:
+        return self.buf[: M * N].view(M, N)
+
+    def reduce_(self, offset_elems: int, elems: int):
+        """All ranks call this on their current stream after writing buf[offset : offset+elems]."""
+        self.hdl.barrier(channel=0)                       # every rank's partials are written
+        capi.allreduce_sum_f16(self.multicast_ptr, self.peer_ptrs, offset_elems, elems, self.rank, self.world)
+        self.hdl.barrier(channel=0)                       # every slice is published
+
+
 class TPLinearW6Ax:
     """A packed W6Ax linear shard living on this rank's GPU.
 
@@ -88,9 +116,49 @@ class TPLinearW6Ax:
 
     def forward(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         M = x.shape[0]
+        if self.mode == "row" and self.world > 1 and getattr(self, "_ar", None) is not None:
+            y = self.forward_peer(x)
+            if out is not None:
+                out.copy_(y)
+                return out
+            return y
         y = capi.linear_w6ax(x, self.w6, self.w_scale, self.N, self.x_bits, self.workspace(M), self.act_round, out)
         if self.mode == "row" and self.world > 1:
             all_reduce_sum(y, self.group)
+        return y
+
+    # ---- row-parallel GEMM overlapped with the peer-memory all-reduce ----
+    def enable_peer_allreduce(self, max_tokens: int, chunks: int = 3, use_multicast: bool = True):
+        """Row-parallel shards: write the partial outputs into symmetric memory and reduce them with our
+        own kernel, token-tile chunk by chunk on a second stream so the reduction of chunk i overlaps the
+        GEMM of chunk i+1.  Collective: every rank must call it."""
+        if self.mode != "row" or self.world == 1:
+            return self
+        self._ar = PeerAllReduce(max_tokens * self.N, self.w6.device, self.group, use_multicast)
+        self._ar_chunks = max(1, chunks)
+        self._comm = torch.cuda.Stream(device=self.w6.device)
+        self._ev = [torch.cuda.Event() for _ in range(self._ar_chunks)]
+        return self
+
+    def forward_peer(self, x: torch.Tensor) -> torch.Tensor:
+        M = x.shape[0]
+        y = self._ar.view(M, self.N)
+        ws = self.workspace(M)
+        tile = 192                                          # the GEMM's token tile: chunk on tile boundaries
+        tiles = (M + tile - 1) // tile
+        nch = min(self._ar_chunks, tiles)
+        cur = torch.cuda.current_stream()
+        self._comm.wait_stream(cur)                         # the buffer may still be read by earlier work
+        row = 0
+        for c in range(nch):
+            rows = min(M - row, ((tiles * (c + 1)) // nch - (tiles * c) // nch) * tile)
+            capi.linear_w6ax(x[row:row + rows], self.w6, self.w_scale, self.N, self.x_bits, ws, self.act_round, y[row:row + rows])
+            self._ev[c].record(cur)
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(self._ev[c])
+                self._ar.reduce_(row * self.N, rows * self.N)
+            row += rows
+        cur.wait_stream(self._comm)
         return y
 
     __call__ = forward

@@ -132,6 +132,33 @@ int flexq_gemm_ref_layout(const int32_t* x_planes, const void* x_scale_half, con
                           const void* w_scale_half, void* d_half, int M, int N, int K, int x_bits,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Producer-side fusions: the kernel that produces a GEMM's activations also quantises
+ * them (native int8 containers + fp32 scales, a6 rounding), feeding flexq_gemm_w6ax directly.
+ *
+ * flexq_rmsnorm_quant_f16 replaces invokeGeneralT5LayerNorm / invokeGeneralAddBiasResidualT5PreLayerNorm with
+ * norm_output_scale != NULL (e2e/src/fastertransformer/kernels/layernorm_kernels.cu:2494-2690, 1852-2110):
+ * if `residual` != NULL it is updated in place to half(x + residual) and normalised instead of x;
+ * y = half((h * rsqrt(mean(h^2) + eps)) * gamma); `normed` (optional, may be NULL) receives y.  K <= 16384.
+ *
+ * flexq_silu_mul_quant_f16 replaces invokeGenericActivation<SiluActivation> with output_scale != NULL
+ * (kernels/activation_kernels.cu:246-440, called from layers/FfnLayer.cc:442-452): y = half(silu(gate) * up),
+ * gate/up rows `ld_in` halves apart (2*K for the halves of a fused gate_up output); `out` optional.       */
+int flexq_rmsnorm_quant_f16(const void* x_half, void* residual_half_inout, const void* gamma_half, float eps,
+                            void* normed_half_out, int8_t* xq, float* sx, int M, int K, int bits, void* stream);
+int flexq_silu_mul_quant_f16(const void* gate_half, const void* up_half, long long ld_in, void* out_half,
+                             int8_t* xq, float* sx, int M, int K, int bits, void* stream);
+
+/* Tensor-parallel reduction of row-parallel partial outputs (replaces ftNcclAllReduceSum,
+ * e2e/src/fastertransformer/utils/nccl_utils.cc:56-68, called after the down / o_proj GEMMs in
+ * layers/TensorParallelSiluFfnLayer.cc:53-56; peer-memory precedent kernels/custom_ar_kernels.cu:139-260).
+ * In-place sum over `world` ranks of `elems` halves starting `offset_elems` into a symmetric allocation:
+ * `multicast_ptr` = the NVSwitch multicast mapping of the allocation (in-switch reduction, multimem PTX),
+ * or NULL to use `peer_ptrs[0..world)` = every rank's mapping of it (host array of device pointers).
+ * elems and offset_elems must be multiples of 8.  This rank reduces and publishes its 1/world slice;
+ * the caller orders ranks with a symmetric-memory barrier on `stream` before and after the call.       */
+int flexq_allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset_elems, size_t elems,
+                            int rank, int world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

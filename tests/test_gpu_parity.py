@@ -353,3 +353,65 @@ def test_host_staged_pipeline_matches_direct_call(capi):
         for l, xh, yh in zip(layers, xs, ys):
             # split-K partial sums meet in fp32 atomics whose order is not fixed: equal up to an fp16 rounding
             assert torch.allclose(l.forward(xh.cuda()).cpu().float(), yh.float(), rtol=2e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------
+# producer-side fusions: fp16 tensor within 1 half-ulp of the formula, integers and
+# scales bit exact given that tensor, and the GEMM fed by them equals the unfused path
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K,bits,resid", [(1, 4096, 6, False), (16, 8192, 6, True), (33, 4096, 8, True), (7, 1024, 6, False),
+                                             (300, 8192, 6, True), (5, 16384, 8, False)])
+def test_rmsnorm_quant(capi, oracle, M, K, bits, resid):
+    rng = np.random.default_rng(M + K + bits)
+    x = (rng.standard_normal((M, K)) * rng.uniform(0.05, 4.0, size=(M, 1))).astype(np.float16)
+    gamma = (1.0 + 0.2 * rng.standard_normal(K)).astype(np.float16)
+    res = rng.standard_normal((M, K)).astype(np.float16) if resid else None
+    y_ref, res_ref = oracle.rmsnorm_half(x, gamma, 1e-5, res)
+    res_t = torch.from_numpy(res).cuda() if resid else None
+    xq, sx, y = capi.rmsnorm_quant(torch.from_numpy(x).cuda(), torch.from_numpy(gamma).cuda(), 1e-5, bits, res_t, want_normed=True)
+    y = y.cpu().numpy()
+    assert oracle.half_ulp_distance(y, y_ref).max() <= 1
+    if resid:
+        assert np.array_equal(res_t.cpu().numpy().view(np.uint16), res_ref.view(np.uint16))   # x + residual: one exact rounding
+    q_ref, s_ref = oracle.quant_act_cuda(y, bits)
+    assert np.array_equal(xq.cpu().numpy().astype(np.int32), q_ref)
+    assert np.array_equal(sx.cpu().numpy()[:, :M].T, s_ref.astype(np.float32))
+    assert np.all(sx.cpu().numpy()[:, M:] == 0)
+    # same integers without asking for the fp16 tensor
+    xq2, sx2, none = capi.rmsnorm_quant(torch.from_numpy(x).cuda(), torch.from_numpy(gamma).cuda(), 1e-5, bits,
+                                        torch.from_numpy(res).cuda() if resid else None)
+    assert none is None and torch.equal(xq2, xq) and torch.equal(sx2, sx)
+
+
+@pytest.mark.parametrize("M,K,bits,fused_layout", [(1, 14336, 8, False), (16, 28672, 8, True), (37, 11008 // 128 * 128, 8, True),
+                                                    (4, 512, 6, False), (600, 14336, 8, True)])
+def test_silu_mul_quant(capi, oracle, M, K, bits, fused_layout):
+    rng = np.random.default_rng(M + K)
+    gu = (rng.standard_normal((M, 2 * K)) * 3.0).astype(np.float16)
+    gu[0, :8] = np.array([0, -0.0, 20, -20, 60, -60, 1e-4, -1e-4], dtype=np.float16)
+    t = torch.from_numpy(gu).cuda()
+    gate, up = (t[:, :K], t[:, K:]) if fused_layout else (t[:, :K].contiguous(), t[:, K:].contiguous())
+    xq, sx, y = capi.silu_mul_quant(gate, up, bits, want_out=True)
+    y = y.cpu().numpy()
+    y_ref = oracle.silu_mul_half(gu[:, :K], gu[:, K:])
+    # __expf / fast division: 1 half-ulp, or absolute 1e-6 for results that are (nearly) denormal
+    ok = (oracle.half_ulp_distance(y, y_ref) <= 1) | (np.abs(y.astype(np.float32) - y_ref.astype(np.float32)) <= 1e-6)
+    assert ok.all(), np.argwhere(~ok)[:4]
+    q_ref, s_ref = oracle.quant_act_cuda(y, bits)
+    assert np.array_equal(xq.cpu().numpy().astype(np.int32), q_ref)
+    assert np.array_equal(sx.cpu().numpy()[:, :M].T, s_ref.astype(np.float32))
+
+
+def test_fused_producers_feed_the_gemm(capi):
+    """norm -> quant -> GEMM through the fused producer == the unfused path on the producer's fp16 output."""
+    dev = torch.device("cuda")
+    torch.manual_seed(3)
+    M, K, N = 48, 4096, 1024
+    x = torch.randn(M, K, device=dev).half()
+    gamma = (1 + 0.1 * torch.randn(K, device=dev)).half()
+    w6, wsc = capi.quant_pack_w6((0.02 * torch.randn(N, K, device=dev)).half())
+    xq, sx, y = capi.rmsnorm_quant(x, gamma, 1e-5, 6, want_normed=True)
+    ws = capi.new_workspace()
+    a = capi.gemm_w6ax(xq, sx, w6, wsc, N, ws)
+    b = capi.linear_w6ax(y, w6, wsc, N, 6, capi.new_workspace(M, K), capi.ROUND_CUDA)
+    assert torch.allclose(a.float(), b.float(), rtol=2e-3, atol=2e-3)
