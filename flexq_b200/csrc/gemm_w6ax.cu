@@ -21,9 +21,9 @@
 // stores fp16 directly; partial segments are summed in an fp32 slot (red.global.add) and the CTA
 // that completes the tile converts, stores and re-zeroes the slot.
 //
-// Warp roles (512 threads): warp 0 = TMA producer (weights), warps 1,2 = MMA issuers (alternate
-// steps; warp 1 also owns the TMEM allocation), warp 3 = TMA producer (activations + scales),
-// warps 4-7 = weight expanders, warps 8-15 = epilogue.
+// Warp roles (512 threads; 640 for the 192-token tile): warp 0 = TMA producer (weights), warps 1,2 = MMA
+// issuers (alternate steps; warp 1 also owns the TMEM allocation), warp 3 = TMA producer (activations +
+// scales), warps 4-7 = weight expanders, warps 8-15 (8-19) = epilogue.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -87,9 +87,10 @@ struct Cfg {
     static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
     static constexpr int SMEM_BYTES = OFF_MISC + 16 + 1024;        // + alignment slack
-    // epilogue warpgroups (2 or 4).  Measured on B200: 4 warpgroups (16 warps, 96 regs) give the same
-    // prefill throughput as 2 (8 warps, 200 regs) -- the epilogue is bound by issue slots / FMA-heavy
-    // pipe, not by latency hiding -- so the simpler 512-thread shape is used everywhere.
+    // epilogue warpgroups.  Measured on B200 (70B shapes, M >= 2048): 3 warpgroups of 64 columns (12 warps, 128 regs)
+    // beat 2 x 96 columns (8 warps, 200 regs) by 3-8 % on the 192-token tile -- one more warp per scheduler to
+    // cover FFMA2 dependencies; 4 x 48 columns are 4 % slower again (per-warp step overhead).  The 128-token
+    // tile and the decode tiles keep 2.
 #ifndef FLEXQ_EPI_WG
 #define FLEXQ_EPI_WG 3
 #endif

@@ -11,3 +11,5 @@ ncu --set full --clock-control none --import-source on -k regex:w6ax_gemm -c 1 -
 ncu --set full --clock-control none --import-source on -k regex:w6ax_gemm -c 1 -s 2 -o gpurun_out/prof_decode_r1 -f python tools/run_case.py --m 16 --n 28672 --k 8192 --iters 3 > gpurun_out/ncu_d.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:quant_act_native -c 1 -s 2 -o gpurun_out/prof_quant_r1 -f python tools/run_case.py --m 2048 --n 8192 --k 28672 --xb 8 --iters 3 --fused > gpurun_out/ncu_q.log 2>&1
 echo done
+for v in NOEPI NOMATH NOLD; do echo "VARIANT $v"; FLEXQ_B200_LIB=$PWD/tools/ubench/ab/lib_$v.so python tools/sweep.py --models 70b --ms 2048 --no-cublas --out gpurun_out/sweep_exp_$v.jsonl 2>&1 | tail -3; done > gpurun_out/experiments_r1.log 2>&1
+python tools/producer_bench.py > gpurun_out/producers_r1.jsonl 2>&1
