@@ -49,6 +49,8 @@ _SIGNATURES = {
     "flexq_gemm_ref_layout": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_rmsnorm_quant_f16": (_i, [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "flexq_silu_mul_quant_f16": (_i, [_vp, _vp, ctypes.c_longlong, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "flexq_set_sm_limit": (_i, [_i]),
+    "flexq_set_allreduce_blocks": (_i, [_i]),
     "flexq_allreduce_sum_f16": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), _sz, _sz, _i, _i, _vp]),
 }
 

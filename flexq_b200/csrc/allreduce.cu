@@ -35,6 +35,8 @@ __device__ __forceinline__ void multimem_st_f16x8(void* mc, const uint4& v) {
 }
 
 constexpr int kArUnroll = 4;
+static int g_ar_blocks = 4 * 148;           // grid cap (set small to stay on SMs the GEMM leaves free)
+void set_allreduce_blocks(int n) { g_ar_blocks = n > 0 ? n : 4 * 148; }
 
 // vec0 .. vec1: this rank's range of 16-byte vectors
 __global__ void __launch_bounds__(256) allreduce_multimem_kernel(__half* mc, long long vec0, long long vec1) {
@@ -93,7 +95,7 @@ int allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset
     if (vec1 <= vec0) return 0;
     const long long work = vec1 - vec0;
     long long nb = (work + 256 * kArUnroll - 1) / (256 * kArUnroll);
-    const int blocks = (int)(nb > 4 * 148 ? 4 * 148 : (nb < 1 ? 1 : nb));
+    const int blocks = (int)(nb > g_ar_blocks ? g_ar_blocks : (nb < 1 ? 1 : nb));
     if (multicast_ptr) {
         allreduce_multimem_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<__half*>(multicast_ptr), vec0, vec1);
         return (int)cudaGetLastError();

@@ -612,6 +612,11 @@ static PFN_tmapEncodeTiled get_encode_fn() {
     return fn;
 }
 
+// Optional cap on the number of CTAs (= SMs) the persistent GEMM occupies, so that a concurrent kernel on
+// another stream (the peer-memory all-reduce of the previous token chunk) finds free SMs.  0 = all SMs.
+static int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -693,7 +698,8 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     p.n_tiles = ceil_div(p.N, kTileN);
     p.m_tiles = ceil_div(p.M, M_TILE);
     {   // pick R rows x Pn columns minimising the per-CTA work (in k-group units); ties -> more rows (more sharing)
-        const int max_ctas = sms < kMaxCtas ? sms : kMaxCtas;
+        int max_ctas = sms < kMaxCtas ? sms : kMaxCtas;
+        if (g_sm_limit > 0 && g_sm_limit < max_ctas) max_ctas = g_sm_limit;
         const long long Umt = (long long)p.n_tiles * p.G;
         long long best = -1;
         for (int R = 1; R <= p.m_tiles && R <= max_ctas; R++) {

@@ -128,7 +128,7 @@ class TPLinearW6Ax:
         return y
 
     # ---- row-parallel GEMM overlapped with the peer-memory all-reduce ----
-    def enable_peer_allreduce(self, max_tokens: int, chunks: int = 3, use_multicast: bool = True):
+    def enable_peer_allreduce(self, max_tokens: int, chunks: int = 3, use_multicast: bool = True, sm_reserve: int = 0):
         """Row-parallel shards: write the partial outputs into symmetric memory and reduce them with our
         own kernel, token-tile chunk by chunk on a second stream so the reduction of chunk i overlaps the
         GEMM of chunk i+1.  Collective: every rank must call it."""
@@ -136,6 +136,7 @@ class TPLinearW6Ax:
             return self
         self._ar = PeerAllReduce(max_tokens * self.N, self.w6.device, self.group, use_multicast)
         self._ar_chunks = max(1, chunks)
+        self._sm_reserve = sm_reserve          # SMs the chunk GEMMs leave free for the concurrent reduction
         self._comm = torch.cuda.Stream(device=self.w6.device)
         self._ev = [torch.cuda.Event() for _ in range(self._ar_chunks)]
         return self
@@ -149,6 +150,10 @@ class TPLinearW6Ax:
         nch = min(self._ar_chunks, tiles)
         cur = torch.cuda.current_stream()
         self._comm.wait_stream(cur)                         # the buffer may still be read by earlier work
+        lib = capi.load()
+        if self._sm_reserve and nch > 1:
+            lib.flexq_set_sm_limit(148 - self._sm_reserve)
+            lib.flexq_set_allreduce_blocks(8 * self._sm_reserve)
         row = 0
         for c in range(nch):
             rows = min(M - row, ((tiles * (c + 1)) // nch - (tiles * c) // nch) * tile)
@@ -158,6 +163,9 @@ class TPLinearW6Ax:
                 self._comm.wait_event(self._ev[c])
                 self._ar.reduce_(row * self.N, rows * self.N)
             row += rows
+        if self._sm_reserve and nch > 1:
+            lib.flexq_set_sm_limit(0)
+            lib.flexq_set_allreduce_blocks(0)
         cur.wait_stream(self._comm)
         return y
 

@@ -156,6 +156,10 @@ int flexq_silu_mul_quant_f16(const void* gate_half, const void* up_half, long lo
  * or NULL to use `peer_ptrs[0..world)` = every rank's mapping of it (host array of device pointers).
  * elems and offset_elems must be multiples of 8.  This rank reduces and publishes its 1/world slice;
  * the caller orders ranks with a symmetric-memory barrier on `stream` before and after the call.       */
+/* Overlap knobs (process-wide): cap the persistent GEMM at n_ctas CTAs (0 = every SM) so that a kernel on
+ * another stream finds free SMs, and cap the all-reduce grid at n_blocks (0 = default).                  */
+int flexq_set_sm_limit(int n_ctas);
+int flexq_set_allreduce_blocks(int n_blocks);
 int flexq_allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset_elems, size_t elems,
                             int rank, int world, void* stream);
 

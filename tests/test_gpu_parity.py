@@ -415,3 +415,46 @@ def test_fused_producers_feed_the_gemm(capi):
     a = capi.gemm_w6ax(xq, sx, w6, wsc, N, ws)
     b = capi.linear_w6ax(y, w6, wsc, N, 6, capi.new_workspace(M, K), capi.ROUND_CUDA)
     assert torch.allclose(a.float(), b.float(), rtol=2e-3, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------
+# model-level quantise -> pack driver and packed checkpoints
+# ------------------------------------------------------------------------------------------
+class _TinyLlamaMLP(torch.nn.Module):
+    def __init__(self, hid=512, inter=1024):
+        super().__init__()
+        self.gate_proj = torch.nn.Linear(hid, inter, bias=False)
+        self.up_proj = torch.nn.Linear(hid, inter, bias=False)
+        self.down_proj = torch.nn.Linear(inter, hid, bias=False)
+        self.lm_head = torch.nn.Linear(hid, 64, bias=False)           # must stay untouched
+
+    def forward(self, x):
+        return self.down_proj(torch.nn.functional.silu(self.gate_proj(x)) * self.up_proj(x))
+
+
+def test_model_pack_roundtrip_and_tp_shards(capi, tmp_path):
+    from flexq_b200 import QuantLinear, model_pack
+    torch.manual_seed(11)
+    model = torch.nn.Sequential(_TinyLlamaMLP(), _TinyLlamaMLP()).half().cuda()
+    x = torch.randn(24, 512, device="cuda").half()
+    model_pack.replace_linears(model)
+    assert isinstance(model[0].down_proj, QuantLinear) and model[0].down_proj.act_quantizer.n_bits == 8     # int_llama_layer.py:35-37
+    assert model[1].gate_proj.act_quantizer.n_bits == 6 and isinstance(model[0].lm_head, torch.nn.Linear)
+    y = model(x)
+    packed = model_pack.pack_model(model)
+    assert sorted(packed) == sorted(f"{i}.{n}" for i in (0, 1) for n in ("gate_proj", "up_proj", "down_proj"))
+    path = str(tmp_path / "tiny.flexq")
+    model_pack.save_packed(packed, path)
+    loaded = model_pack.load_packed(path)
+    model2 = torch.nn.Sequential(_TinyLlamaMLP(), _TinyLlamaMLP()).half().cuda()
+    model_pack.load_into(model2, loaded)
+    assert torch.allclose(model2(x).float(), y.float(), rtol=2e-3, atol=2e-3)
+    # TP shards of a packed entry == packing the sharded weight (bit for bit)
+    e = packed["0.gate_proj"]
+    w = model[0].gate_proj.weight
+    for mode in ("column", "row"):
+        for rank in range(2):
+            sh = model_pack.shard_packed(e, mode, rank, 2)
+            ws = w[rank * 512:(rank + 1) * 512] if mode == "column" else w[:, rank * 256:(rank + 1) * 256]
+            w6_ref, sc_ref = capi.quant_pack_w6(ws.contiguous())
+            assert torch.equal(sh["w6"], w6_ref) and torch.equal(sh["w_scale"], sc_ref), (mode, rank)

@@ -40,6 +40,18 @@ def test_capi_argument_validation_without_gpu():
     assert lib.flexq_gemm_w6ax(one, one, one, one, one, 1, 128, 128, one, 16, None) == -4         # workspace
     assert lib.flexq_quant_act(one, one, one, 4, 256, 7, 0, None) == -2                           # bits
     assert lib.flexq_bit_packing_i32(one, one, 12, 128, 6, None) == -1                            # ragged planes
+    # fused producers and the peer all-reduce
+    assert lib.flexq_rmsnorm_quant_f16(None, None, one, 1e-5, None, one, one, 4, 256, 6, None) == -3
+    assert lib.flexq_rmsnorm_quant_f16(one, None, one, 1e-5, None, one, one, 4, 200, 6, None) == -1       # K % 128
+    assert lib.flexq_rmsnorm_quant_f16(one, None, one, 1e-5, None, one, one, 4, 32768, 6, None) == -1     # K > 16384
+    assert lib.flexq_rmsnorm_quant_f16(one, None, one, 1e-5, None, one, one, 4, 256, 5, None) == -2
+    assert lib.flexq_silu_mul_quant_f16(one, None, 256, None, one, one, 4, 256, 8, None) == -3
+    assert lib.flexq_silu_mul_quant_f16(one, one, 128, None, one, one, 4, 256, 8, None) == -1             # ld_in < K
+    assert lib.flexq_allreduce_sum_f16(None, None, 0, 1024, 0, 2, None) == -3
+    assert lib.flexq_allreduce_sum_f16(one, None, 0, 1023, 0, 2, None) == -1                               # 16-byte vectors
+    assert lib.flexq_allreduce_sum_f16(one, None, 0, 1024, 2, 2, None) == -1                               # rank >= world
+    assert lib.flexq_allreduce_sum_f16(one, None, 0, 1024, 0, 1, None) == 0                                # world 1: nothing to do
+    assert lib.flexq_set_sm_limit(0) == 0 and lib.flexq_set_allreduce_blocks(0) == 0
 
 
 def _params(bits, axes):
@@ -146,3 +158,40 @@ def test_tp_shard_validation():
         tp.shard_weight(w, "row", 0, 3)          # K/128 = 8 groups not divisible by 3
     with pytest.raises(ValueError):
         tp.shard_weight(w, "diag", 0, 2)
+
+
+def test_model_pack_driver_structure_and_packed_shards_cpu():
+    """f1 host logic that needs no GPU: the linear swap follows the reference's bit policy
+    (int_llama_layer.py:31-43) and packed entries shard on tile / group boundaries."""
+    from flexq_b200 import QuantLinear, model_pack
+
+    class MLP(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj, self.up_proj = nn.Linear(256, 512, bias=False), nn.Linear(256, 512, bias=False)
+            self.down_proj, self.lm_head = nn.Linear(512, 256, bias=False), nn.Linear(256, 32, bias=False)
+
+    m = model_pack.replace_linears(nn.ModuleList([MLP(), MLP()]))
+    for blk in m:
+        assert isinstance(blk.gate_proj, QuantLinear) and blk.gate_proj.act_quantizer.n_bits == 6
+        assert blk.down_proj.act_quantizer.n_bits == 8 and blk.down_proj.weight_quantizer.n_bits == 6
+        assert blk.gate_proj.use_weight_quant and blk.gate_proj.use_act_quant and blk.gate_proj.kernel_supported()
+        assert isinstance(blk.lm_head, nn.Linear) and not isinstance(blk.lm_head, QuantLinear)
+    m2 = model_pack.replace_linears(nn.ModuleList([MLP()]), flex_linear_quant=False)
+    assert m2[0].down_proj.act_quantizer.n_bits == 6
+
+    N, K = 512, 384
+    nt, G = N // 128, K // 128
+    w6 = torch.arange(nt * G, dtype=torch.int32).repeat_interleave(12288).to(torch.uint8)       # byte = tile*G + group
+    e = {"w6": w6, "w_scale": torch.arange(G * N, dtype=torch.float16).view(G, N), "N": N, "K": K, "x_bits": 6, "bias": None}
+    c = model_pack.shard_packed(e, "column", 1, 2)
+    assert c["N"] == 256 and c["K"] == K and c["w6"].numel() == 2 * G * 12288
+    assert c["w6"].view(2, G, 12288)[:, :, 0].tolist() == [[6, 7, 8], [9, 10, 11]]
+    assert torch.equal(c["w_scale"], e["w_scale"][:, 256:])
+    r = model_pack.shard_packed(e, "row", 2, 3)
+    assert r["K"] == 128 and r["w6"].view(nt, 1, 12288)[:, 0, 0].tolist() == [2, 5, 8, 11]
+    assert torch.equal(r["w_scale"], e["w_scale"][2:3])
+    with pytest.raises(ValueError):
+        model_pack.shard_packed(e, "column", 0, 8)          # 512 / 8 is not a whole tile
+    with pytest.raises(ValueError):
+        model_pack.shard_packed(e, "row", 0, 2)             # 3 groups do not split in 2
