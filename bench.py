@@ -171,14 +171,43 @@ def main():
     total_ops = sum(2.0 * M_TOKENS * N * K for _, N, K, _, _ in LAYERS)
     stream = torch.cuda.current_stream()
 
+    # Row-parallel reduction.  tp >= 8: our peer-memory all-reduce (flexq_allreduce_sum_f16 over NVLink / NVSwitch
+    # symmetric memory), two token chunks so the reduction of chunk 0 overlaps the GEMM of chunk 1 on 8 SMs the
+    # GEMM leaves free (measured: 201 us vs 287 us with NCCL for down_proj at tp=8).  tp = 2, 4: NCCL (as fast or faster there).
+    # FLEXQ_BENCH_AR=nccl|peer overrides.  Any failure to set up symmetric memory falls back to NCCL.
+    ar_mode = "nccl"
+    want_peer = os.environ.get("FLEXQ_BENCH_AR", "peer" if world >= 8 else "nccl") == "peer"
+    ar_chunks = int(os.environ.get("FLEXQ_BENCH_AR_CHUNKS", "2"))
+    if world > 1 and want_peer:
+        try:
+            for lin in layers:
+                lin.enable_peer_allreduce(M_TOKENS, chunks=ar_chunks, use_multicast=(world == 8), sm_reserve=8)
+            ar_mode = "peer"
+        except Exception as e:                       # noqa: BLE001
+            for lin in layers:
+                lin._ar = None
+            if rank == 0:
+                print(f"[bench] peer all-reduce unavailable ({str(e)[:100]}); using NCCL", file=sys.stderr)
+        flag = torch.tensor([1.0 if ar_mode == "peer" else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # all ranks must agree
+        if flag.item() < 1.0:
+            ar_mode = "nccl"
+            for lin in layers:
+                lin._ar = None
+
     def step_device():
         for lin, x, o in zip(layers, x_dev, outs):
-            lin.forward(x, o)
+            if getattr(lin, "_ar", None) is not None:
+                lin.forward(x)                                # result stays in the symmetric buffer
+            else:
+                lin.forward(x, o)
 
     # end to end: pinned host activations in, pinned host outputs back, through the host-buffer front end
     # (H2D / kernels / D2H on three streams, per-layer staging buffers -- flexq_b200/host_io.py)
     from flexq_b200.host_io import HostStagedLinears
-    pipe = HostStagedLinears(layers, M_TOKENS, dev)
+    # replicated (all-reduced) outputs go back to the host from rank 0 only; sharded outputs from every rank
+    copy_out = [not (mode == "row" and world > 1 and rank != 0) for _, _, _, mode, _ in LAYERS]
+    pipe = HostStagedLinears(layers, M_TOKENS, dev, copy_out)
 
     def timed_e2e(steps, warmup):
         for _ in range(warmup):
@@ -259,14 +288,17 @@ def main():
         cpu = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample}
 
     h2d = sum(x.numel() * 2 for x in x_host)
-    d2h = sum(y.numel() * 2 for y in y_host)
+    d2h = sum(y.numel() * 2 for y, c in zip(y_host, copy_out) if c)
     line = {
         "metric": "W6A6 GEMM TOPS (2*M*N*K/t), llama2-70b linear layers", "value": total_ops / (ms_step * 1e-3) / 1e12,
         "unit": "TOPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "tokens": M_TOKENS, "parallelism": f"tp{world}",
                    "l2": "per-step working set (384 MB packed weights + activations) exceeds the 126 MB L2",
-                   "step": "fused activation quantise + W6A6 GEMM per layer" + (" + NCCL all-reduce on row-parallel layers" if world > 1 else "")},
+                   "step": "fused activation quantise + W6A6 GEMM per layer" + (
+                       "" if world == 1 else " + NCCL all-reduce on row-parallel layers" if ar_mode == "nccl" else
+                       " + peer-memory all-reduce (own kernel, NVLink symmetric memory) on row-parallel layers, 2 token chunks "
+                       "overlapped with the GEMM")},
         "e2e": {"value": total_ops / (ms_e2e * 1e-3) / 1e12, "unit": "TOPS", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "pinned host x -> H2D -> fused quantise + GEMM -> D2H -> pinned host y, every layer every step; "

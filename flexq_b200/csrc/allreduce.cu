@@ -82,6 +82,129 @@ __global__ void __launch_bounds__(256) allreduce_peer_kernel(PeerPtrs peers, lon
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-shot variant for decode-sized reductions (M x N fp16 <= ~1 MB): ONE kernel, no stream barriers.
+// Every rank keeps its partial in a symmetric allocation and owns two flag words per peer.  Arrive:
+// store-release the call's epoch into my slot on every peer, then spin (acquire, bounded) until every
+// peer's slot in my array has reached it.  Reduce: read all ranks' partials (peer loads, fp32 sum in rank
+// order -> every rank gets identical bits) into a private output.  Done: the same exchange once more, so
+// that no rank overwrites its partial while a peer still reads it.  The epoch is a device-side counter, so
+// the call is CUDA-graph capturable.  (The reference's FasterTransformer fork has the same idea in
+// kernels/custom_ar_kernels.cu:139-260, oneShotAllReduceKernel.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct FlagPtrs {
+    uint32_t* p[8];
+};
+
+// flags layout per rank (uint32): [0, 8) arrive[src], [8, 16) done[src], [16] epoch of the last finished call,
+// [17] CTA ticket.  Everything the protocol needs lives on the device, so the call can sit in a CUDA graph.
+constexpr int kFlagDone = 8, kFlagEpoch = 16, kFlagTicket = 17;
+
+template <int WORLD>
+__global__ void __launch_bounds__(256) allreduce_oneshot_kernel(PeerPtrs data, FlagPtrs flags, long long nvec, int rank,
+                                                                uint4* __restrict__ out) {
+    // the partial was written by earlier work of this stream (PDL: wait for it before publishing)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t* mine = flags.p[rank];
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(mine + kFlagEpoch) + 1u;   // bumped by the last CTA, after every CTA read it
+    if (blockIdx.x == 0 && threadIdx.x < WORLD) {
+        __threadfence_system();
+        st_release_sys(flags.p[threadIdx.x] + rank, epoch);                  // arrive: my slot in peer `threadIdx.x`'s array
+    }
+    if (threadIdx.x < WORLD) {
+        uint32_t spins = 0;
+        while ((int32_t)(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {
+            if (++spins > (1u << 24)) __trap();                              // a rank is missing: fail instead of hanging
+        }
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4 in[WORLD];
+#pragma unroll
+        for (int r = 0; r < WORLD; r++) in[r] = __ldcv(reinterpret_cast<const uint4*>(data.p[r]) + i);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < WORLD; r++) {
+            const __half2* h = reinterpret_cast<const __half2*>(&in[r]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __half22float2(h[j]);
+                acc[2 * j] += f.x;
+                acc[2 * j + 1] += f.y;
+            }
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+        out[i] = o;
+    }
+    // closing phase: nobody may overwrite its partial (the next GEMM of this stream) while a peer still reads it.
+    // The last CTA of this rank tells the peers "I am done reading" and waits for the same from all of them.
+    __syncthreads();
+    __shared__ uint32_t s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(mine + kFlagTicket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < WORLD) {
+            st_release_sys(flags.p[threadIdx.x] + kFlagDone + rank, epoch);
+            uint32_t spins = 0;
+            while ((int32_t)(ld_acquire_sys(mine + kFlagDone + threadIdx.x) - epoch) < 0) {
+                if (++spins > (1u << 24)) __trap();
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mine[kFlagTicket] = 0u;
+            *reinterpret_cast<volatile uint32_t*>(mine + kFlagEpoch) = epoch;
+        }
+    }
+}
+
+int allreduce_oneshot_f16(void* const* data_ptrs, void* const* flag_ptrs, size_t elems, int rank, int world, void* out,
+                          cudaStream_t stream) {
+    if (!data_ptrs || !flag_ptrs || !out) return FLEXQ_ERR_NULL;
+    if ((world != 2 && world != 4 && world != 8) || rank < 0 || rank >= world) return FLEXQ_ERR_BAD_SHAPE;
+    if (elems == 0 || elems % 8) return FLEXQ_ERR_BAD_SHAPE;
+    PeerPtrs dp{};
+    FlagPtrs fp{};
+    for (int r = 0; r < world; r++) {
+        if (!data_ptrs[r] || !flag_ptrs[r]) return FLEXQ_ERR_NULL;
+        dp.p[r] = reinterpret_cast<__half*>(data_ptrs[r]);
+        fp.p[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+    }
+    const long long nvec = (long long)(elems / 8);
+    long long nb = (nvec + 255) / 256;
+    const int blocks = (int)(nb > 64 ? 64 : nb);           // all CTAs co-resident: the ticket protocol relies on it
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    uint4* o = reinterpret_cast<uint4*>(out);
+    switch (world) {
+        case 2: return (int)cudaLaunchKernelEx(&cfg, allreduce_oneshot_kernel<2>, dp, fp, nvec, rank, o);
+        case 4: return (int)cudaLaunchKernelEx(&cfg, allreduce_oneshot_kernel<4>, dp, fp, nvec, rank, o);
+        default: return (int)cudaLaunchKernelEx(&cfg, allreduce_oneshot_kernel<8>, dp, fp, nvec, rank, o);
+    }
+}
+
 int allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset_elems, size_t elems, int rank, int world,
                       cudaStream_t stream) {
     if (world < 1 || world > 8 || rank < 0 || rank >= world) return FLEXQ_ERR_BAD_SHAPE;

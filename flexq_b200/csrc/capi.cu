@@ -15,6 +15,7 @@ int gemm_w6ax(const int8_t*, const float*, const uint8_t*, const __half*, __half
 int gemm_w6ax_groupsums(const int8_t*, const uint8_t*, int32_t*, int, int, int, cudaStream_t);
 int rmsnorm_quant(const __half*, __half*, const __half*, float, __half*, int8_t*, float*, int, int, int, cudaStream_t);
 int silu_mul_quant(const __half*, const __half*, long long, __half*, int8_t*, float*, int, int, int, cudaStream_t);
+int allreduce_oneshot_f16(void* const*, void* const*, size_t, int, int, void*, cudaStream_t);
 void set_sm_limit(int);
 void set_allreduce_blocks(int);
 int allreduce_sum_f16(void*, void* const*, size_t, size_t, int, int, cudaStream_t);
@@ -144,6 +145,10 @@ int flexq_silu_mul_quant_f16(const void* gate, const void* up, long long ld_in, 
     return silu_mul_quant((const __half*)gate, (const __half*)up, ld_in, (__half*)out, xq, sx, M, K, bits, (cudaStream_t)stream);
 }
 
+int flexq_allreduce_oneshot_f16(void* const* data_ptrs, void* const* flag_ptrs, size_t elems, int rank, int world, void* out,
+                                void* stream) {
+    return allreduce_oneshot_f16(data_ptrs, flag_ptrs, elems, rank, world, out, (cudaStream_t)stream);
+}
 int flexq_set_sm_limit(int n_ctas) { set_sm_limit(n_ctas); return 0; }
 int flexq_set_allreduce_blocks(int n_blocks) { set_allreduce_blocks(n_blocks); return 0; }
 

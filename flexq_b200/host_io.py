@@ -14,8 +14,11 @@ import torch
 
 
 class HostStagedLinears:
-    def __init__(self, layers, max_tokens: int, device: torch.device):
+    def __init__(self, layers, max_tokens: int, device: torch.device, copy_out=None):
+        """`copy_out[i]` False skips the D2H of layer i on this rank (tensor parallel: the all-reduced output of
+        a row-parallel layer is identical on every rank, only one of them needs to hand it to the host)."""
         self.layers = list(layers)
+        self.copy_out = list(copy_out) if copy_out is not None else [True] * len(self.layers)
         self.dev = device
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
         self.x_dev = [torch.empty(max_tokens, l.K, dtype=torch.float16, device=device) for l in self.layers]
@@ -46,7 +49,8 @@ class HostStagedLinears:
                 self.ev_comp[i].record(self.s_comp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_comp[i])
-                yh.copy_(yd, non_blocking=True)
+                if self.copy_out[i]:
+                    yh.copy_(yd, non_blocking=True)
                 self.ev_out[i].record(self.s_out)
         self.passes += 1
 

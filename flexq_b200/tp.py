@@ -83,6 +83,38 @@ class PeerAllReduce:
         self.hdl.barrier(channel=0)                       # every slice is published
 
 
+class PeerOneShotAllReduce:
+    """Decode-sized fp16 sum all-reduce in ONE kernel (flexq_allreduce_oneshot_f16): the partial lives in a
+    symmetric allocation, arrival / completion are signalled through per-peer flag words, the epoch is a
+    device-side counter (CUDA-graph capturable, no stream barriers).  `partial(M, N)` is where the producer
+    (the row-parallel GEMM) writes; `reduce(M, N)` sums into a private tensor."""
+
+    def __init__(self, max_elems: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.max_elems = (max_elems + 7) // 8 * 8
+        self.data = symm.empty(self.max_elems, dtype=torch.float16, device=device)
+        self.flags = symm.empty(32, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.h_data = symm.rendezvous(self.data, self.group)
+        self.h_flags = symm.rendezvous(self.flags, self.group)
+        self.data_ptrs = [int(p) for p in self.h_data.buffer_ptrs]
+        self.flag_ptrs = [int(p) for p in self.h_flags.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        self.h_flags.barrier(channel=0)                    # every rank's flags are zero before anyone publishes
+        torch.cuda.synchronize(device)
+
+    def partial(self, M: int, N: int) -> torch.Tensor:
+        return self.data[: M * N].view(M, N)
+
+    def reduce(self, M: int, N: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(M, N, dtype=torch.float16, device=self.data.device)
+        capi.allreduce_oneshot_f16(self.data_ptrs, self.flag_ptrs, M * N, self.rank, self.world, out)
+        return out
+
+
 class TPLinearW6Ax:
     """A packed W6Ax linear shard living on this rank's GPU.
 
@@ -116,6 +148,11 @@ class TPLinearW6Ax:
 
     def forward(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         M = x.shape[0]
+        os_ = getattr(self, "_oneshot", None)
+        if self.mode == "row" and self.world > 1 and os_ is not None and M * self.N <= os_.max_elems and (M * self.N) % 8 == 0:
+            part = os_.partial(M, self.N)
+            capi.linear_w6ax(x, self.w6, self.w_scale, self.N, self.x_bits, self.workspace(M), self.act_round, part)
+            return os_.reduce(M, self.N, out)
         if self.mode == "row" and self.world > 1 and getattr(self, "_ar", None) is not None:
             y = self.forward_peer(x)
             if out is not None:
@@ -126,6 +163,13 @@ class TPLinearW6Ax:
         if self.mode == "row" and self.world > 1:
             all_reduce_sum(y, self.group)
         return y
+
+    def enable_oneshot_allreduce(self, max_tokens: int = 64):
+        """Decode: reduce row-parallel partials of up to `max_tokens` rows with the one-kernel peer all-reduce.
+        Collective: every rank must call it."""
+        if self.mode == "row" and self.world > 1:
+            self._oneshot = PeerOneShotAllReduce(max_tokens * self.N, self.w6.device, self.group)
+        return self
 
     # ---- row-parallel GEMM overlapped with the peer-memory all-reduce (SURVEY.md 8(f4)) ----
     def enable_peer_allreduce(self, max_tokens: int, chunks: int = 3, use_multicast: bool = True, sm_reserve: int = 0):

@@ -156,6 +156,16 @@ int flexq_silu_mul_quant_f16(const void* gate_half, const void* up_half, long lo
  * or NULL to use `peer_ptrs[0..world)` = every rank's mapping of it (host array of device pointers).
  * elems and offset_elems must be multiples of 8.  This rank reduces and publishes its 1/world slice;
  * the caller orders ranks with a symmetric-memory barrier on `stream` before and after the call.       */
+/* One-kernel variant for decode-sized reductions (no stream barriers, CUDA-graph capturable;
+ * oneShotAllReduceKernel of kernels/custom_ar_kernels.cu:139-190 is the reference's counterpart).
+ * `data_ptrs[r]` / `flag_ptrs[r]` = rank r's mapping of a symmetric buffer holding that rank's partial (elems
+ * halves) and of a zero-initialised symmetric array of 32 uint32 (arrive/done slots, epoch, ticket).
+ * `out` (private, elems halves) receives the sum; the call returns after every rank has finished reading,
+ * so the partial may be overwritten by the next kernel of the stream.  A rank that never arrives makes the
+ * others trap after a bounded spin instead of hanging.  elems % 8 == 0, at most 64 CTAs.                */
+int flexq_allreduce_oneshot_f16(void* const* data_ptrs, void* const* flag_ptrs, size_t elems, int rank, int world,
+                                void* out_half, void* stream);
+
 /* Overlap knobs (process-wide): cap the persistent GEMM at n_ctas CTAs (0 = every SM) so that a kernel on
  * another stream finds free SMs, and cap the all-reduce grid at n_blocks (0 = default).                  */
 int flexq_set_sm_limit(int n_ctas);
