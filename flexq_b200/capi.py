@@ -49,6 +49,7 @@ _SIGNATURES = {
     "flexq_gemm_ref_layout": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_rmsnorm_quant_f16": (_i, [_vp, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "flexq_silu_mul_quant_f16": (_i, [_vp, _vp, ctypes.c_longlong, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "flexq_allreduce_sum_synced_f16": (_i, [_vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _sz, _sz, _i, _i, _vp]),
     "flexq_allreduce_oneshot_f16": (_i, [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _sz, _i, _i, _vp, _vp]),
     "flexq_set_sm_limit": (_i, [_i]),
     "flexq_set_allreduce_blocks": (_i, [_i]),
@@ -246,6 +247,14 @@ def allreduce_sum_f16(multicast_ptr: int, peer_ptrs, offset_elems: int, elems: i
     arr = (ctypes.c_void_p * 8)(*([int(p) for p in peer_ptrs] + [0] * (8 - len(peer_ptrs)))) if peer_ptrs else None
     check(load().flexq_allreduce_sum_f16(ctypes.c_void_p(int(multicast_ptr or 0)), arr, offset_elems, elems, rank, world, _stream()),
           "flexq_allreduce_sum_f16")
+
+
+def allreduce_sum_synced_f16(multicast_ptr: int, peer_ptrs, flag_ptrs, offset_elems: int, elems: int, rank: int, world: int):
+    """Two-shot all-reduce with the cross-rank hand-shake inside the kernel (no stream barriers)."""
+    arr = (ctypes.c_void_p * 8)(*([int(p) for p in peer_ptrs] + [0] * (8 - len(peer_ptrs))))
+    f = (ctypes.c_void_p * 8)(*([int(p) for p in flag_ptrs] + [0] * (8 - len(flag_ptrs))))
+    check(load().flexq_allreduce_sum_synced_f16(ctypes.c_void_p(int(multicast_ptr or 0)), arr, f, offset_elems, elems, rank, world,
+                                                _stream()), "flexq_allreduce_sum_synced_f16")
 
 
 def allreduce_oneshot_f16(data_ptrs, flag_ptrs, elems: int, rank: int, world: int, out: torch.Tensor):

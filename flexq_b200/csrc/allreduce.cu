@@ -21,6 +21,61 @@ struct PeerPtrs {
     __half* p[8];
 };
 
+// ---- cross-rank hand-shake through flag words in symmetric memory (used by the synced two-shot kernels and the
+// one-shot kernel).  Layout per rank (uint32): [0, 8) arrive[src], [8, 16) done[src], [16] epoch of the last finished
+// call, [17] CTA ticket.  The epoch is a device-side counter, so calls can sit in a CUDA graph.
+struct FlagPtrs {
+    uint32_t* p[8];
+};
+constexpr int kFlagDone = 8, kFlagEpoch = 16, kFlagTicket = 17;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_until(const uint32_t* f, uint32_t epoch) {
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+        if (++spins > (1u << 24)) __trap();                                  // a rank is missing: fail instead of hanging
+    }
+}
+// Opening: tell every peer that this rank's data is in place, wait until every peer said the same.  Returns the epoch.
+__device__ __forceinline__ uint32_t ar_open(const FlagPtrs& flags, int rank, int world) {
+    uint32_t* mine = flags.p[rank];
+    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(mine + kFlagEpoch) + 1u;   // bumped by the last CTA, after every CTA read it
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(flags.p[threadIdx.x] + rank, epoch);
+    }
+    if ((int)threadIdx.x < world) spin_until(mine + threadIdx.x, epoch);
+    __syncthreads();
+    return epoch;
+}
+// Closing: the last CTA of this rank tells the peers that this rank is done (reading / publishing) and waits for all.
+__device__ __forceinline__ void ar_close(const FlagPtrs& flags, int rank, int world, uint32_t epoch) {
+    uint32_t* mine = flags.p[rank];
+    __threadfence_system();
+    __syncthreads();
+    __shared__ uint32_t s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(mine + kFlagTicket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        if ((int)threadIdx.x < world) {
+            st_release_sys(flags.p[threadIdx.x] + kFlagDone + rank, epoch);
+            spin_until(mine + kFlagDone + threadIdx.x, epoch);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mine[kFlagTicket] = 0u;
+            *reinterpret_cast<volatile uint32_t*>(mine + kFlagEpoch) = epoch;
+        }
+    }
+}
+
 __device__ __forceinline__ uint4 multimem_ld_reduce_f16x8(const void* mc) {
     uint4 v;
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
@@ -35,11 +90,18 @@ __device__ __forceinline__ void multimem_st_f16x8(void* mc, const uint4& v) {
 }
 
 constexpr int kArUnroll = 4;
-static int g_ar_blocks = 4 * 148;           // grid cap (set small to stay on SMs the GEMM leaves free)
-void set_allreduce_blocks(int n) { g_ar_blocks = n > 0 ? n : 4 * 148; }
+// 0: free-running grid (up to 4 x 148 blocks of 256 threads).  n > 0: at most n blocks of 1024 threads -- used while a
+// persistent GEMM (one CTA per SM, all of its shared memory) runs on the other SMs: every SM that hosts even one small
+// block of ours is lost to the GEMM, so the reduction is packed onto as few SMs as the GEMM leaves free.
+static int g_ar_blocks = 0;
+void set_allreduce_blocks(int n) { g_ar_blocks = n > 0 ? n : 0; }
 
 // vec0 .. vec1: this rank's range of 16-byte vectors
-__global__ void __launch_bounds__(256) allreduce_multimem_kernel(__half* mc, long long vec0, long long vec1) {
+__global__ void __launch_bounds__(1024) allreduce_multimem_kernel(__half* mc, long long vec0, long long vec1, FlagPtrs flags, int rank,
+                                                                 int world) {
+    const bool synced = flags.p[0] != nullptr;
+    uint32_t epoch = 0;
+    if (synced) epoch = ar_open(flags, rank, world);
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = vec0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint4* base = reinterpret_cast<uint4*>(mc);
@@ -51,10 +113,14 @@ __global__ void __launch_bounds__(256) allreduce_multimem_kernel(__half* mc, lon
         for (int u = 0; u < kArUnroll; u++) multimem_st_f16x8(base + i + u * stride, v[u]);
     }
     for (; i < vec1; i += stride) multimem_st_f16x8(base + i, multimem_ld_reduce_f16x8(base + i));
+    if (synced) ar_close(flags, rank, world, epoch);
 }
 
 template <int WORLD>
-__global__ void __launch_bounds__(256) allreduce_peer_kernel(PeerPtrs peers, long long vec0, long long vec1) {
+__global__ void __launch_bounds__(1024) allreduce_peer_kernel(PeerPtrs peers, long long vec0, long long vec1, FlagPtrs flags, int rank) {
+    const bool synced = flags.p[0] != nullptr;
+    uint32_t epoch = 0;
+    if (synced) epoch = ar_open(flags, rank, WORLD);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = vec0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vec1; i += stride) {
         uint4 in[WORLD];
@@ -80,6 +146,7 @@ __global__ void __launch_bounds__(256) allreduce_peer_kernel(PeerPtrs peers, lon
 #pragma unroll
         for (int r = 0; r < WORLD; r++) *(reinterpret_cast<uint4*>(peers.p[r]) + i) = out;
     }
+    if (synced) ar_close(flags, rank, WORLD, epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -92,41 +159,12 @@ __global__ void __launch_bounds__(256) allreduce_peer_kernel(PeerPtrs peers, lon
 // the call is CUDA-graph capturable.  (The reference's FasterTransformer fork has the same idea in
 // kernels/custom_ar_kernels.cu:139-260, oneShotAllReduceKernel.)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-struct FlagPtrs {
-    uint32_t* p[8];
-};
-
-// flags layout per rank (uint32): [0, 8) arrive[src], [8, 16) done[src], [16] epoch of the last finished call,
-// [17] CTA ticket.  Everything the protocol needs lives on the device, so the call can sit in a CUDA graph.
-constexpr int kFlagDone = 8, kFlagEpoch = 16, kFlagTicket = 17;
-
 template <int WORLD>
 __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(PeerPtrs data, FlagPtrs flags, long long nvec, int rank,
                                                                 uint4* __restrict__ out) {
     // the partial was written by earlier work of this stream (PDL: wait for it before publishing)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    uint32_t* mine = flags.p[rank];
-    const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(mine + kFlagEpoch) + 1u;   // bumped by the last CTA, after every CTA read it
-    if (blockIdx.x == 0 && threadIdx.x < WORLD) {
-        __threadfence_system();
-        st_release_sys(flags.p[threadIdx.x] + rank, epoch);                  // arrive: my slot in peer `threadIdx.x`'s array
-    }
-    if (threadIdx.x < WORLD) {
-        uint32_t spins = 0;
-        while ((int32_t)(ld_acquire_sys(mine + threadIdx.x) - epoch) < 0) {
-            if (++spins > (1u << 24)) __trap();                              // a rank is missing: fail instead of hanging
-        }
-    }
-    __syncthreads();
+    const uint32_t epoch = ar_open(flags, rank, WORLD);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         uint4 in[WORLD];
@@ -151,26 +189,8 @@ __global__ void __launch_bounds__(256) allreduce_oneshot_kernel(PeerPtrs data, F
         for (int j = 0; j < 4; j++) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
         out[i] = o;
     }
-    // closing phase: nobody may overwrite its partial (the next GEMM of this stream) while a peer still reads it.
-    // The last CTA of this rank tells the peers "I am done reading" and waits for the same from all of them.
-    __syncthreads();
-    __shared__ uint32_t s_last;
-    if (threadIdx.x == 0) s_last = (atomicAdd(mine + kFlagTicket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (s_last) {
-        if (threadIdx.x < WORLD) {
-            st_release_sys(flags.p[threadIdx.x] + kFlagDone + rank, epoch);
-            uint32_t spins = 0;
-            while ((int32_t)(ld_acquire_sys(mine + kFlagDone + threadIdx.x) - epoch) < 0) {
-                if (++spins > (1u << 24)) __trap();
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mine[kFlagTicket] = 0u;
-            *reinterpret_cast<volatile uint32_t*>(mine + kFlagEpoch) = epoch;
-        }
-    }
+    // closing phase: nobody may overwrite its partial (the next GEMM of this stream) while a peer still reads it
+    ar_close(flags, rank, WORLD, epoch);
 }
 
 int allreduce_oneshot_f16(void* const* data_ptrs, void* const* flag_ptrs, size_t elems, int rank, int world, void* out,
@@ -205,22 +225,30 @@ int allreduce_oneshot_f16(void* const* data_ptrs, void* const* flag_ptrs, size_t
     }
 }
 
-int allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset_elems, size_t elems, int rank, int world,
-                      cudaStream_t stream) {
+int allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, void* const* flag_ptrs, size_t offset_elems, size_t elems, int rank,
+                      int world, cudaStream_t stream) {
     if (world < 1 || world > 8 || rank < 0 || rank >= world) return FLEXQ_ERR_BAD_SHAPE;
     if (!multicast_ptr && !peer_ptrs) return FLEXQ_ERR_NULL;
     if (elems % 8 || offset_elems % 8) return FLEXQ_ERR_BAD_SHAPE;             // 16-byte vectors
     if (elems == 0 || world == 1) return 0;
+    FlagPtrs fp{};
+    if (flag_ptrs)
+        for (int r = 0; r < world; r++) {
+            if (!flag_ptrs[r]) return FLEXQ_ERR_NULL;
+            fp.p[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
+        }
     const long long nvec = (long long)(elems / 8), v_off = (long long)(offset_elems / 8);
     const long long per = (nvec + world - 1) / world;
     const long long lo = per * rank, hi = per * (rank + 1);
     const long long vec0 = v_off + (lo < nvec ? lo : nvec), vec1 = v_off + (hi < nvec ? hi : nvec);
-    if (vec1 <= vec0) return 0;
-    const long long work = vec1 - vec0;
-    long long nb = (work + 256 * kArUnroll - 1) / (256 * kArUnroll);
-    const int blocks = (int)(nb > g_ar_blocks ? g_ar_blocks : (nb < 1 ? 1 : nb));
+    if (vec1 <= vec0 && !flag_ptrs) return 0;              // synced calls always launch: the peers wait for this rank
+    const long long work = vec1 > vec0 ? vec1 - vec0 : 0;
+    const int threads = g_ar_blocks > 0 ? 1024 : 256;
+    const long long cap = g_ar_blocks > 0 ? g_ar_blocks : 4 * 148;
+    long long nb = (work + threads * kArUnroll - 1) / (threads * kArUnroll);
+    const int blocks = (int)(nb > cap ? cap : (nb < 1 ? 1 : nb));
     if (multicast_ptr) {
-        allreduce_multimem_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<__half*>(multicast_ptr), vec0, vec1);
+        allreduce_multimem_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<__half*>(multicast_ptr), vec0, vec1, fp, rank, world);
         return (int)cudaGetLastError();
     }
     PeerPtrs pp{};
@@ -229,9 +257,9 @@ int allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset
         pp.p[r] = reinterpret_cast<__half*>(peer_ptrs[r]);
     }
     switch (world) {
-        case 2: allreduce_peer_kernel<2><<<blocks, 256, 0, stream>>>(pp, vec0, vec1); break;
-        case 4: allreduce_peer_kernel<4><<<blocks, 256, 0, stream>>>(pp, vec0, vec1); break;
-        case 8: allreduce_peer_kernel<8><<<blocks, 256, 0, stream>>>(pp, vec0, vec1); break;
+        case 2: allreduce_peer_kernel<2><<<blocks, threads, 0, stream>>>(pp, vec0, vec1, fp, rank); break;
+        case 4: allreduce_peer_kernel<4><<<blocks, threads, 0, stream>>>(pp, vec0, vec1, fp, rank); break;
+        case 8: allreduce_peer_kernel<8><<<blocks, threads, 0, stream>>>(pp, vec0, vec1, fp, rank); break;
         default: return FLEXQ_ERR_BAD_SHAPE;
     }
     return (int)cudaGetLastError();

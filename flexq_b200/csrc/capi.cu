@@ -18,7 +18,7 @@ int silu_mul_quant(const __half*, const __half*, long long, __half*, int8_t*, fl
 int allreduce_oneshot_f16(void* const*, void* const*, size_t, int, int, void*, cudaStream_t);
 void set_sm_limit(int);
 void set_allreduce_blocks(int);
-int allreduce_sum_f16(void*, void* const*, size_t, size_t, int, int, cudaStream_t);
+int allreduce_sum_f16(void*, void* const*, void* const*, size_t, size_t, int, int, cudaStream_t);
 int gemm_w6ax_trace(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, long long*, int, cudaStream_t);
 }  // namespace flexq
 
@@ -154,7 +154,12 @@ int flexq_set_allreduce_blocks(int n_blocks) { set_allreduce_blocks(n_blocks); r
 
 int flexq_allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, size_t offset_elems, size_t elems, int rank, int world,
                             void* stream) {
-    return allreduce_sum_f16(multicast_ptr, peer_ptrs, offset_elems, elems, rank, world, (cudaStream_t)stream);
+    return allreduce_sum_f16(multicast_ptr, peer_ptrs, nullptr, offset_elems, elems, rank, world, (cudaStream_t)stream);
+}
+int flexq_allreduce_sum_synced_f16(void* multicast_ptr, void* const* peer_ptrs, void* const* flag_ptrs, size_t offset_elems,
+                                   size_t elems, int rank, int world, void* stream) {
+    if (!flag_ptrs) return FLEXQ_ERR_NULL;
+    return allreduce_sum_f16(multicast_ptr, peer_ptrs, flag_ptrs, offset_elems, elems, rank, world, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -72,12 +72,24 @@ class PeerAllReduce:
         self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         self.multicast_ptr = mc if use_multicast else 0
+        # flag words for the in-kernel hand-shake (zeroed everywhere before anyone uses them)
+        self.flags = symm.empty(32, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.h_flags = symm.rendezvous(self.flags, self.group)
+        self.flag_ptrs = [int(p) for p in self.h_flags.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        self.h_flags.barrier(channel=0)
+        torch.cuda.synchronize(device)
+        self.in_kernel_sync = True
 
     def view(self, M: int, N: int) -> torch.Tensor:
         return self.buf[: M * N].view(M, N)
 
     def reduce_(self, offset_elems: int, elems: int):
         """All ranks call this on their current stream after writing buf[offset : offset+elems]."""
+        if self.in_kernel_sync:                           # one kernel: arrive / reduce + publish / done
+            capi.allreduce_sum_synced_f16(self.multicast_ptr, self.peer_ptrs, self.flag_ptrs, offset_elems, elems, self.rank, self.world)
+            return
         self.hdl.barrier(channel=0)                       # every rank's partials are written
         capi.allreduce_sum_f16(self.multicast_ptr, self.peer_ptrs, offset_elems, elems, self.rank, self.world)
         self.hdl.barrier(channel=0)                       # every slice is published
@@ -197,7 +209,7 @@ class TPLinearW6Ax:
         lib = capi.load()
         if self._sm_reserve and nch > 1:
             lib.flexq_set_sm_limit(148 - self._sm_reserve)
-            lib.flexq_set_allreduce_blocks(8 * self._sm_reserve)
+            lib.flexq_set_allreduce_blocks(self._sm_reserve)
         row = 0
         for c in range(nch):
             rows = min(M - row, ((tiles * (c + 1)) // nch - (tiles * c) // nch) * tile)

@@ -156,6 +156,13 @@ int flexq_silu_mul_quant_f16(const void* gate_half, const void* up_half, long lo
  * or NULL to use `peer_ptrs[0..world)` = every rank's mapping of it (host array of device pointers).
  * elems and offset_elems must be multiples of 8.  This rank reduces and publishes its 1/world slice;
  * the caller orders ranks with a symmetric-memory barrier on `stream` before and after the call.       */
+/* Same reduction with the cross-rank ordering inside the kernel: `flag_ptrs[r]` = rank r's mapping of a
+ * zero-initialised symmetric array of 32 uint32; the kernel first waits until every rank has entered it (all
+ * partials written) and returns only after every rank has published its slice -- no barriers on the stream,
+ * CUDA-graph capturable.  Bounded spins: a missing rank makes the others trap instead of hanging.        */
+int flexq_allreduce_sum_synced_f16(void* multicast_ptr, void* const* peer_ptrs, void* const* flag_ptrs,
+                                   size_t offset_elems, size_t elems, int rank, int world, void* stream);
+
 /* One-kernel variant for decode-sized reductions (no stream barriers, CUDA-graph capturable;
  * oneShotAllReduceKernel of kernels/custom_ar_kernels.cu:139-190 is the reference's counterpart).
  * `data_ptrs[r]` / `flag_ptrs[r]` = rank r's mapping of a symmetric buffer holding that rank's partial (elems

@@ -74,7 +74,7 @@ x = torch.randn(M, K, device=dev).half()
 lin = tp.TPLinearW6Ax.from_packed(w6, wsc, N, K, "row", 6, rank, world)
 y_nccl = lin.forward(x).clone()
 us_nccl = timeit(lambda: lin.forward(x))
-for chunks, reserve, mc in ((1, 0, False), (2, 8, False), (2, 16, False), (3, 16, False), (2, 8, True)):
+for chunks, reserve, mc in ((1, 0, False), (2, 8, False), (2, 16, False), (3, 16, False), (2, 8, True), (2, 16, True), (3, 16, True)):
     lin.enable_peer_allreduce(M, chunks=chunks, use_multicast=mc, sm_reserve=reserve)
     y_peer = lin.forward(x).clone()
     torch.cuda.synchronize()
