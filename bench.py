@@ -34,6 +34,10 @@ M_TOKENS = 2048
 LAYERS = [("attn_o_8192x8192", 8192, 8192, "row", 6),
           ("mlp_gate_28672x8192", 28672, 8192, "column", 6),
           ("mlp_down_8192x28672", 8192, 28672, "row", 6)]
+# dram__bytes_read.sum + dram__bytes_write.sum of the captured launch (ncu --set full, profiles/ncu_prefill_r1.txt)
+NCU_TRAFFIC_BYTES = 223.15e6 + 110.06e6
+NCU_TRAFFIC_NOTE = ("ncu capture of the 28672x8192 M=2048 launch: 223.2 MB read + 110.1 MB written; algorithmic bytes of that "
+                    "launch 314 MB (packed W 176 + X 17 + D 117 + scales 4)")
 WORKLOAD = "llama2-70b linears {8192x8192, 28672x8192, 8192x28672} W6A6 g128 prefill M=2048"
 
 
@@ -273,7 +277,8 @@ def main():
         peak = 2.0 * bf16_tf                       # kind::i8 issues at twice the bf16 rate on sm_100
         achieved = total_ops / world / (ms_gemm * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOPS", "frac": achieved / peak,
-                "traffic": None, "kernel": "w6ax_gemm_kernel<M_TILE=192,GP=1>", "launches_per_step": len(LAYERS),
+                "traffic": NCU_TRAFFIC_BYTES if world == 1 else None, "traffic_note": NCU_TRAFFIC_NOTE,
+                "kernel": "w6ax_gemm_kernel<M_TILE=192,GP=1>", "launches_per_step": len(LAYERS),
                 "avg_launch_ms": ms_gemm / len(LAYERS),
                 "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({src}); int8 dense = 2x bf16 dense on sm_100"}
 

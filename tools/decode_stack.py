@@ -57,6 +57,9 @@ def main():
     ap.add_argument("--batches", default="1,2,4,8,16")
     ap.add_argument("--layers", type=int, default=0, help="override layer count (memory)")
     ap.add_argument("--fuse-gate-up", action="store_true", help="gate and up as one N=2*inter GEMM")
+    ap.add_argument("--chain", action="store_true",
+                    help="realistic producer chain: (residual+)RMSNorm+quant -> qkv, quant -> o, residual+RMSNorm+quant -> gate_up, "
+                         "SiLU*up+quant -> down (needs --fuse-gate-up); fp16 side runs rms_norm / silu*mul / matmul")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     hid, inter, qkv, layers = MODELS[a.model]
@@ -95,11 +98,49 @@ def main():
                 for w in lf:
                     torch.matmul(xs[w.shape[1]], w.t(), out=outs[(w.shape[0], w.shape[1])])
 
+        if a.chain:
+            assert a.fuse_gate_up
+            gamma = torch.ones(hid, device=dev).half()
+            h0 = torch.randn(B, hid, device=dev).half()
+            attn = torch.randn(B, hid, device=dev).half()
+            gws = capi.new_workspace()
+
+            def run_q():                                     # noqa: F811
+                h = h0.clone()
+                resid = None
+                for (wqkv, wo, wgu, wdn) in packed:
+                    xq, sx, _ = capi.rmsnorm_quant(h, gamma, 1e-5, 6, resid)          # (residual +) norm + quant
+                    capi.gemm_w6ax(xq, sx, wqkv[0], wqkv[1], wqkv[2], gws, outs[(wqkv[2], wqkv[3])])
+                    resid = h if resid is None else resid                              # residual stream lives in `resid`
+                    o = capi.linear_w6ax(attn, wo[0], wo[1], wo[2], 6, wss[wo[3]], capi.ROUND_CUDA, outs[(wo[2], wo[3])])
+                    xq, sx, _ = capi.rmsnorm_quant(o, gamma, 1e-5, 6, resid)          # resid += o; norm; quant
+                    gu = capi.gemm_w6ax(xq, sx, wgu[0], wgu[1], wgu[2], gws, outs[(wgu[2], wgu[3])])
+                    xq, sx, _ = capi.silu_mul_quant(gu[:, :inter], gu[:, inter:], 8)
+                    h = capi.gemm_w6ax(xq, sx, wdn[0], wdn[1], wdn[2], gws, outs[(wdn[2], wdn[3])])
+                return h
+
+            def run_f():                                     # noqa: F811
+                h = h0.clone()
+                resid = None
+                F = torch.nn.functional
+                for (wqkv, wo, wgu, wdn) in fp16:
+                    resid = h if resid is None else resid + h
+                    x = F.rms_norm(resid, (hid,), gamma, 1e-5)
+                    torch.matmul(x, wqkv.t(), out=outs[(wqkv.shape[0], wqkv.shape[1])])
+                    o = torch.matmul(attn, wo.t(), out=outs[(wo.shape[0], wo.shape[1])])
+                    resid = resid + o
+                    x = F.rms_norm(resid, (hid,), gamma, 1e-5)
+                    gu = torch.matmul(x, wgu.t(), out=outs[(wgu.shape[0], wgu.shape[1])])
+                    act = F.silu(gu[:, :inter]) * gu[:, inter:]
+                    h = torch.matmul(act, wdn.t(), out=outs[(wdn.shape[0], wdn.shape[1])])
+                return h
+
         tq, tf = graph_us(run_q), graph_us(run_f)
-        rec = {"model": a.model, "layers": layers, "batch": B, "fuse_gate_up": a.fuse_gate_up, "linears_per_layer": len(shapes),
+        rec = {"model": a.model, "layers": layers, "batch": B, "fuse_gate_up": a.fuse_gate_up, "chain": a.chain, "linears_per_layer": len(shapes),
                "w6ax_us": tq, "w6ax_tok_s": B / tq * 1e6, "fp16_us": tf, "fp16_tok_s": B / tf * 1e6, "speedup_vs_fp16": tf / tq,
                "weight_gbs": wbytes / tq / 1e3, "hbm_frac": wbytes / tq / 1e3 / hbm,
-               "note": "linear stack only (no attention / KV / norms); synthetic weights"}
+               "note": ("decoder layer without attention / KV: norms, residuals, SiLU*up and all linears; synthetic weights" if a.chain
+                        else "linear stack only (no attention / KV / norms); synthetic weights")}
         results.append(rec)
         print(json.dumps(rec), flush=True)
     if a.out:

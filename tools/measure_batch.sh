@@ -13,3 +13,6 @@ ncu --set full --clock-control none --import-source on -k regex:quant_act_native
 echo done
 for v in NOEPI NOMATH NOLD; do echo "VARIANT $v"; FLEXQ_B200_LIB=$PWD/tools/ubench/ab/lib_$v.so python tools/sweep.py --models 70b --ms 2048 --no-cublas --out gpurun_out/sweep_exp_$v.jsonl 2>&1 | tail -3; done > gpurun_out/experiments_r1.log 2>&1
 python tools/producer_bench.py > gpurun_out/producers_r1.jsonl 2>&1
+python tools/decode_stack.py --model llama2-70b --layers 40 --fuse-gate-up --chain --batches 1,4,16 > gpurun_out/decode_70b_chain.jsonl 2> gpurun_out/decode_70b_chain.err
+python tools/decode_stack.py --model llama3-8b --fuse-gate-up --chain --batches 1,4,16 > gpurun_out/decode_l3_8b_chain.jsonl 2> gpurun_out/decode_l3_8b_chain.err
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.txt 2>&1
