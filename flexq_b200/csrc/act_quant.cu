@@ -208,8 +208,8 @@ __device__ __forceinline__ void quant_store(const uint4& raw, int m, int v, int 
 // generalT5LayerNormFlexQFusion / generalAddResidualT5LayerNormFlexQFusion (layernorm_kernels.cu:2494-2517,
 // 1852-1905): residual' = half(clamp(x + residual)); var = sum(h^2) / K in fp32; rstd = rsqrtf(var + eps);
 // y = half(clamp((float(h) * rstd) * float(gamma))); then the a6 quantiser on y.
-template <int U, bool RESID>
-__global__ void __launch_bounds__(256) rmsnorm_quant_kernel(const uint4* __restrict__ x, uint4* __restrict__ resid,
+template <int U, bool RESID, int MAXT>
+__global__ void __launch_bounds__(MAXT) rmsnorm_quant_kernel(const uint4* __restrict__ x, uint4* __restrict__ resid,
                                                             const uint4* __restrict__ gamma, uint4* __restrict__ normed,
                                                             int8_t* __restrict__ xq, float* __restrict__ sx, float eps, int M, int K,
                                                             int ldsx, int bits) {
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) rmsnorm_quant_kernel(const uint4* __restr
     const int lane16 = threadIdx.x & 15;
     const int nvec = K >> 3;
     if (m >= M) {
-        for (int v = threadIdx.x; v < nvec; v += 256)
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x)
             if ((v & 15) == 0) sx[(size_t)(v >> 4) * ldsx + m] = 0.f;
         return;
     }
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) rmsnorm_quant_kernel(const uint4* __restr
     float ss = 0.f;
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        const int v = u * 256 + threadIdx.x;
+        const int v = u * blockDim.x + threadIdx.x;
         raw[u] = make_uint4(0, 0, 0, 0);
         if (v < nvec) {
             raw[u] = __ldg(x + (size_t)m * nvec + v);
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) rmsnorm_quant_kernel(const uint4* __restr
             }
         }
     }
-    __shared__ float warp_sum[8];
+    __shared__ float warp_sum[32];
     __shared__ float s_rstd;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -259,15 +259,14 @@ __global__ void __launch_bounds__(256) rmsnorm_quant_kernel(const uint4* __restr
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; w++) t += warp_sum[w];
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_sum[w];
         s_rstd = rsqrtf(t / (float)K + eps);
     }
     __syncthreads();
     const float rstd = s_rstd;
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        const int v = u * 256 + threadIdx.x;
+        const int v = u * blockDim.x + threadIdx.x;
         if (v >= nvec) break;
         const uint4 gg = __ldg(gamma + v);
         __half2* h = reinterpret_cast<__half2*>(&raw[u]);
@@ -331,10 +330,10 @@ __global__ void __launch_bounds__(256) silu_mul_quant_kernel(const __half* __res
 }
 
 template <typename Kern, typename... Args>
-static int launch_pdl(Kern kern, dim3 grid, cudaStream_t stream, Args... args) {
+static int launch_pdl(Kern kern, dim3 grid, int threads, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3(threads);
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -350,15 +349,27 @@ int rmsnorm_quant(const __half* x, __half* residual, const __half* gamma, float 
     if (M <= 0 || K < kGroup || K % kGroup || K > 256 * 8 * 8) return FLEXQ_ERR_BAD_SHAPE;
     if (bits != 6 && bits != 8) return FLEXQ_ERR_BAD_BITS;
     const int ldsx = ceil4(M);
-    const int need = (K / 8 + 255) / 256;
+    // few rows (decode): one vector per thread, up to 1024 threads per row -- the shortest dependent chain, since only M
+    // rows are in flight; many rows (prefill): 256 threads x up to 8 vectors, several rows resident per SM
+    const int nvec = K / 8;
+    const int tmax = ldsx >= 128 ? 256 : 1024;
+    const int threads = nvec >= tmax ? tmax : ((nvec + 31) / 32) * 32;
+    const int need = (nvec + threads - 1) / threads;
     const dim3 grid(ldsx);
     const uint4* xv = reinterpret_cast<const uint4*>(x);
     uint4* rv = reinterpret_cast<uint4*>(residual);
     const uint4* gv = reinterpret_cast<const uint4*>(gamma);
     uint4* nv = reinterpret_cast<uint4*>(normed);
 #define FQ_RMS(U_)                                                                                                              \
-    return residual ? launch_pdl(rmsnorm_quant_kernel<U_, true>, grid, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits) \
-                    : launch_pdl(rmsnorm_quant_kernel<U_, false>, grid, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits)
+    return residual ? launch_pdl(rmsnorm_quant_kernel<U_, true, 256>, grid, threads, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits) \
+                    : launch_pdl(rmsnorm_quant_kernel<U_, false, 256>, grid, threads, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits)
+    if (tmax == 1024) {       // decode-sized: need is 1 (K <= 8192) or 2
+        if (need <= 1)
+            return residual ? launch_pdl(rmsnorm_quant_kernel<1, true, 1024>, grid, threads, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits)
+                            : launch_pdl(rmsnorm_quant_kernel<1, false, 1024>, grid, threads, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits);
+        return residual ? launch_pdl(rmsnorm_quant_kernel<2, true, 1024>, grid, threads, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits)
+                        : launch_pdl(rmsnorm_quant_kernel<2, false, 1024>, grid, threads, stream, xv, rv, gv, nv, xq, sx, eps, M, K, ldsx, bits);
+    }
     if (need <= 1) { FQ_RMS(1); }
     if (need <= 2) { FQ_RMS(2); }
     if (need <= 4) { FQ_RMS(4); }
@@ -377,8 +388,8 @@ int silu_mul_quant(const __half* gate, const __half* up, long long ld_in, __half
     const int per_block = 256 * (big ? 2 : 1);
     const dim3 grid(ldsx, (nvec + per_block - 1) / per_block);
     uint4* ov = reinterpret_cast<uint4*>(out);
-    if (big) return launch_pdl(silu_mul_quant_kernel<2>, grid, stream, gate, up, ld_in, ov, xq, sx, M, K, ldsx, bits);
-    return launch_pdl(silu_mul_quant_kernel<1>, grid, stream, gate, up, ld_in, ov, xq, sx, M, K, ldsx, bits);
+    if (big) return launch_pdl(silu_mul_quant_kernel<2>, grid, 256, stream, gate, up, ld_in, ov, xq, sx, M, K, ldsx, bits);
+    return launch_pdl(silu_mul_quant_kernel<1>, grid, 256, stream, gate, up, ld_in, ov, xq, sx, M, K, ldsx, bits);
 }
 
 // Reference plane layout.  Lane l (0..15) of a group owns k = 8l..8l+7; plane word k32 = l/4 is
