@@ -4,6 +4,8 @@ Bar: bit-exact for every integer/byte result (quantised ints, packed words, INT3
 sums); fp16 outputs within a stated tolerance of (a) the exact real value of the kernel's
 formula and (b) the reference's fake-quant path.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -458,3 +460,39 @@ def test_model_pack_roundtrip_and_tp_shards(capi, tmp_path):
             ws = w[rank * 512:(rank + 1) * 512] if mode == "column" else w[:, rank * 256:(rank + 1) * 256]
             w6_ref, sc_ref = capi.quant_pack_w6(ws.contiguous())
             assert torch.equal(sh["w6"], w6_ref) and torch.equal(sh["w_scale"], sc_ref), (mode, rank)
+
+
+# ------------------------------------------------------------------------------------------
+# every work-decomposition regime of the GEMM against an exact float64 evaluation on the GPU:
+# decode and mid M (stream-K: tiles split over several CTAs, fp32 atomics), large M (several passes over whole
+# tiles, bit-reproducible), ragged M / N
+# ------------------------------------------------------------------------------------------
+def _exact_w6ax(capi, xq, sx, w6, wsc, N):
+    M, K = xq.shape
+    G = K // 128
+    wq = capi.w6_to_i8(w6, N, K).double().view(N, G, 128)
+    xg = xq.double().view(M, G, 128)
+    S = torch.einsum("mgk,ngk->gmn", xg, wq)                               # exact integer sums in float64
+    return torch.einsum("gmn,gm,gn->mn", S, sx[:, :M].double(), wsc.double())
+
+
+@pytest.mark.parametrize("M,N,K,xb", [(16, 4096, 4096, 6), (8, 1024, 8192, 8), (100, 4096, 4096, 6), (192, 8192, 2048, 6),
+                                       (256, 8192, 4096, 8), (300, 4096, 8192, 6), (448, 2048, 4096, 6), (512, 8192, 8192, 6),
+                                       (1000, 4096, 2048, 6), (2048, 8192, 1024, 6), (2500, 1000, 1024, 8), (3000, 28672, 1024, 6)])
+def test_gemm_every_decomposition_vs_exact(capi, M, N, K, xb):
+    dev = torch.device("cuda")
+    torch.manual_seed(M + N + K)
+    w6, wsc = capi.quant_pack_w6((0.02 * torch.randn(N, K, device=dev)).half())
+    x = torch.randn(M, K, device=dev).half()
+    xq, sx = capi.quant_act(x, xb)
+    ws = capi.new_workspace()
+    ref = _exact_w6ax(capi, xq, sx, w6, wsc, N)
+    outs = [capi.gemm_w6ax(xq, sx, w6, wsc, N, ws).clone() for _ in range(3)]
+    torch.cuda.synchronize()
+    for o in outs:
+        err = (o.double() - ref).abs()
+        assert (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() <= RMS_REL_TOL
+        assert (err.max() / ref.abs().mean()).item() <= MAXABS_REL_TOL
+    if M >= 2048:
+        # several passes over whole tiles: no split-K atomics, the same bits every time
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
