@@ -129,6 +129,61 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------
+# --config c1: BASELINE.json configs[0], the reference's own CPU-runnable case, as a side record
+# --------------------------------------------------------------------------------------------
+def run_c1():
+    """nn.Linear(4096, 4096, bias=False) default init under torch.manual_seed(0), x = randn(16, 4096), W6A6 g128:
+    the reference's CPU fake-quant forward (faithful = weights re-quantised per call, and pre-quantised) on all host
+    cores beside the fused CUDA path; outputs compared."""
+    from oracle.fakequant_torch import FakeQuantLinearCPU      # baseline leg
+    from flexq_b200 import QuantLinear, model_pack
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4096, 4096, bias=False)
+    x = torch.randn(16, 4096)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    def cpu_ms(mod, n):
+        mod(x)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            y = mod(x)
+        return (time.perf_counter() - t0) / n * 1e3, y
+
+    ms_f, y_cpu = cpu_ms(FakeQuantLinearCPU(lin.weight.detach(), 6, faithful=True), 5)
+    ms_p, _ = cpu_ms(FakeQuantLinearCPU(lin.weight.detach(), 6, faithful=False), 20)
+    q = QuantLinear(lin.half().cuda(), model_pack.default_quant_params(6, True), model_pack.default_quant_params(6, False))
+    q.set_quant_state(True, True)
+    xg = x.half().cuda()
+    y = q(xg)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        q(xg)
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        q(xg)
+    for _ in range(5):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 200 * 1e3
+    ref = y_cpu.double()
+    err = (y.double().cpu() - ref)
+    line = {"config": "C1: QuantLinear W6A6 g128, nn.Linear(4096,4096) seed 0, x = randn(16,4096)",
+            "cpu_faithful_ms": ms_f, "cpu_prequantized_ms": ms_p, "cpu_cores": cores, "cpu_kind": "port (oracle/fakequant_torch.py, fp32)",
+            "gpu_fused_us_graph": us, "speedup_vs_faithful": ms_f * 1e3 / us, "speedup_vs_prequantized": ms_p * 1e3 / us,
+            "rms_rel_vs_cpu_fp32": float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()),
+            "note": "GPU path quantises in fp16 (module dtype) and rounds activations half-away; CPU port is the fp32 fake-quant forward"}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
 def main():
@@ -138,7 +193,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="flexq_b200", choices=["flexq_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=["c3", "c1"], help="c3 = the bench workload (default); c1 = side record")
     args = ap.parse_args()
+    if args.config == "c1":
+        run_c1()
+        return
     if args.impl == "reference":
         run_reference_arm(args)
         return

@@ -53,6 +53,31 @@ def replace_linears(model: nn.Module, weight_quant_params: dict | None = None, a
     return model
 
 
+# ---- model-level helpers with the reference's names and semantics (algorithm/flexq_quantize/utils.py) --------------
+def set_quant_state(model: nn.Module, weight_quant: bool = False, act_quant: bool = False):
+    """utils.py:125-131 -- switch every QuantLinear of the model."""
+    for m in model.modules():
+        if isinstance(m, QuantLinear):
+            m.set_quant_state(weight_quant, act_quant)
+
+
+@torch.no_grad()
+def weight_quant_inplace(model: nn.Module):
+    """utils.py:116-123 -- overwrite every QuantLinear weight by its fake-quantised value (the weight quantiser also
+    records the scales it used).  The real-quant path repacks lazily from the new weight."""
+    for m in model.modules():
+        if isinstance(m, QuantLinear):
+            m.weight = m.weight_quantizer(m.weight)
+            m.use_temporary_parameter = False
+
+
+def register_scales_and_zeros(model: nn.Module):
+    """utils.py:60-63 -- keep the weight quantisers' last scales / zero points as buffers."""
+    for m in model.modules():
+        if isinstance(m, QuantLinear):
+            m.weight_quantizer.register_scales_and_zeros()
+
+
 @torch.no_grad()
 def pack_model(model: nn.Module) -> dict:
     """{qualified name: packed entry} for every kernel-backed QuantLinear of ``model`` (weights on the GPU)."""

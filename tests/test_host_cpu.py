@@ -179,6 +179,15 @@ def test_model_pack_driver_structure_and_packed_shards_cpu():
         assert isinstance(blk.lm_head, nn.Linear) and not isinstance(blk.lm_head, QuantLinear)
     m2 = model_pack.replace_linears(nn.ModuleList([MLP()]), flex_linear_quant=False)
     assert m2[0].down_proj.act_quantizer.n_bits == 6
+    # reference-named model helpers (flexq_quantize/utils.py:60-63,116-131)
+    model_pack.set_quant_state(m2, False, False)
+    assert not m2[0].gate_proj.use_weight_quant and not m2[0].gate_proj.use_act_quant
+    w_before = m2[0].gate_proj.weight.clone()
+    model_pack.weight_quant_inplace(m2)
+    wq = m2[0].gate_proj.weight
+    assert not torch.equal(wq, w_before) and torch.equal(m2[0].gate_proj.weight_quantizer(wq.clone()), wq)   # idempotent
+    model_pack.register_scales_and_zeros(m2)
+    assert m2[0].gate_proj.weight_quantizer.scales.shape == (512 * 256 // 128, 1)
 
     N, K = 512, 384
     nt, G = N // 128, K // 128
