@@ -234,13 +234,14 @@ def main():
     total_ops = sum(2.0 * M_TOKENS * N * K for _, N, K, _, _ in LAYERS)
     stream = torch.cuda.current_stream()
 
-    # Row-parallel reduction.  tp >= 8: our peer-memory all-reduce (flexq_allreduce_sum_f16 over NVLink / NVSwitch
-    # symmetric memory), two token chunks so the reduction of chunk 0 overlaps the GEMM of chunk 1 on 8 SMs the
-    # GEMM leaves free (measured: 201 us vs 287 us with NCCL for down_proj at tp=8).  tp = 2, 4: NCCL (as fast or faster there).
+    # Row-parallel reduction: our peer-memory all-reduce (flexq_allreduce_sum_synced_f16 over NVLink / NVSwitch symmetric
+    # memory).  tp = 8: NVSwitch multicast path, two token chunks so the reduction of chunk 0 overlaps the GEMM of chunk 1
+    # on 8 SMs the GEMM leaves free (measured: 196 us vs 288 us with NCCL for down_proj).  tp = 2, 4: peer-pointer path
+    # after the whole GEMM (the 32 MB reduction alone: 69 / 96 us vs NCCL 83 / 119 us).
     # FLEXQ_BENCH_AR=nccl|peer overrides.  Any failure to set up symmetric memory falls back to NCCL.
     ar_mode = "nccl"
-    want_peer = os.environ.get("FLEXQ_BENCH_AR", "peer" if world >= 8 else "nccl") == "peer"
-    ar_chunks = int(os.environ.get("FLEXQ_BENCH_AR_CHUNKS", "2"))
+    want_peer = os.environ.get("FLEXQ_BENCH_AR", "peer") == "peer"
+    ar_chunks = int(os.environ.get("FLEXQ_BENCH_AR_CHUNKS", "2" if world >= 8 else "1"))
     if world > 1 and want_peer:
         try:
             for lin in layers:
@@ -361,8 +362,8 @@ def main():
                    "l2": "per-step working set (384 MB packed weights + activations) exceeds the 126 MB L2",
                    "step": "fused activation quantise + W6A6 GEMM per layer" + (
                        "" if world == 1 else " + NCCL all-reduce on row-parallel layers" if ar_mode == "nccl" else
-                       " + peer-memory all-reduce (own kernel, NVLink symmetric memory) on row-parallel layers, 2 token chunks "
-                       "overlapped with the GEMM")},
+                       " + peer-memory all-reduce (own kernel, NVLink symmetric memory) on row-parallel layers"
+                       + (f", {ar_chunks} token chunks overlapped with the GEMM" if ar_chunks > 1 else ""))},
         "e2e": {"value": total_ops / (ms_e2e * 1e-3) / 1e12, "unit": "TOPS", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "path": "pinned host x -> H2D -> fused quantise + GEMM -> D2H -> pinned host y, every layer every step; "
