@@ -184,7 +184,8 @@ class TPLinearW6Ax:
         return self
 
     # ---- row-parallel GEMM overlapped with the peer-memory all-reduce ----
-    def enable_peer_allreduce(self, max_tokens: int, chunks: int = 3, use_multicast: bool = True, sm_reserve: int = 0):
+    def enable_peer_allreduce(self, max_tokens: int, chunks: int = 3, use_multicast: bool = True, sm_reserve: int = 0,
+                              first_frac: float = 0.0):
         """Row-parallel shards: write the partial outputs into symmetric memory and reduce them with our
         own kernel, token-tile chunk by chunk on a second stream so the reduction of chunk i overlaps the
         GEMM of chunk i+1.  Collective: every rank must call it."""
@@ -193,6 +194,7 @@ class TPLinearW6Ax:
         self._ar = PeerAllReduce(max_tokens * self.N, self.w6.device, self.group, use_multicast)
         self._ar_chunks = max(1, chunks)
         self._sm_reserve = sm_reserve          # SMs the chunk GEMMs leave free for the concurrent reduction
+        self._first_frac = first_frac          # 2 chunks: share of the token tiles in the first one (0 = even split)
         self._comm = torch.cuda.Stream(device=self.w6.device)
         self._ev = [torch.cuda.Event() for _ in range(self._ar_chunks)]
         return self
@@ -212,7 +214,11 @@ class TPLinearW6Ax:
             lib.flexq_set_allreduce_blocks(self._sm_reserve)
         row = 0
         for c in range(nch):
-            rows = min(M - row, ((tiles * (c + 1)) // nch - (tiles * c) // nch) * tile)
+            if nch == 2 and self._first_frac > 0:
+                t0 = max(1, min(tiles - 1, round(tiles * self._first_frac)))
+                rows = min(M - row, (t0 if c == 0 else tiles - t0) * tile)
+            else:
+                rows = min(M - row, ((tiles * (c + 1)) // nch - (tiles * c) // nch) * tile)
             capi.linear_w6ax(x[row:row + rows], self.w6, self.w_scale, self.N, self.x_bits, ws, self.act_round, y[row:row + rows])
             self._ev[c].record(cur)
             with torch.cuda.stream(self._comm):

@@ -74,12 +74,12 @@ x = torch.randn(M, K, device=dev).half()
 lin = tp.TPLinearW6Ax.from_packed(w6, wsc, N, K, "row", 6, rank, world)
 y_nccl = lin.forward(x).clone()
 us_nccl = timeit(lambda: lin.forward(x))
-for chunks, reserve, mc in ((1, 0, False), (2, 8, False), (2, 16, False), (3, 16, False), (2, 8, True), (2, 16, True), (3, 16, True)):
-    lin.enable_peer_allreduce(M, chunks=chunks, use_multicast=mc, sm_reserve=reserve)
+for chunks, reserve, mc, ff in ((1, 0, True, 0.0), (2, 8, True, 0.0), (2, 8, True, 0.36), (2, 8, True, 0.27), (2, 16, True, 0.36), (3, 8, True, 0.0)):
+    lin.enable_peer_allreduce(M, chunks=chunks, use_multicast=mc, sm_reserve=reserve, first_frac=ff)
     y_peer = lin.forward(x).clone()
     torch.cuda.synchronize()
     err = (y_peer.float() - y_nccl.float()).abs().max().item()
     us_peer = timeit(lambda: lin.forward(x))
     if rank == 0:
-        print(f"row-parallel down 8192x{K} M={M}: NCCL {us_nccl:.1f} us, peer-overlapped chunks={chunks} reserve={reserve} mc={mc} {us_peer:.1f} us, max diff {err:.4g}", flush=True)
+        print(f"row-parallel down 8192x{K} M={M}: NCCL {us_nccl:.1f} us, peer-overlapped chunks={chunks} reserve={reserve} mc={mc} first={ff} {us_peer:.1f} us, max diff {err:.4g}", flush=True)
 dist.destroy_process_group()
