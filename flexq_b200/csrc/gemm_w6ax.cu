@@ -368,10 +368,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     } else {
         // ===================== epilogue =====================
-        // Accumulators are re-armed with the bit pattern of 1.5*2^23 before every group, so the
-        // int32 sum 4*S read back from TMEM *is* the float (kMagicF + 4*S): one FMA with the
-        // per-row weight scale removes the bias exactly (kMagicF*sw is exact in fp32 for an
-        // fp16-valued sw) and a second FMA applies the per-token scale and accumulates.
+        // The int32 group sum 4*S read back from TMEM is turned into the float (kMagicF + 4*S) bit-wise (magic_f32:
+        // LOP3 or integer add; with FLEXQ_REARM the accumulators are pre-biased in TMEM instead).  One FMA with the
+        // per-row weight scale removes the bias exactly (kMagicF*sw is exact in fp32 for an fp16-valued sw) and a
+        // second FMA applies the per-token scale and accumulates.
         reg_alloc<C::EPI_REGS>();
         constexpr int CPT = C::CPT, CH = C::CH;
         constexpr uint32_t kMagicI = 0x4B400000u;
