@@ -6,5 +6,6 @@ Public surface mirrors the reference's: ``QuantLinear`` / ``UniformAffineQuantiz
 from . import capi  # noqa: F401
 from .quantizer import UniformAffineQuantizer  # noqa: F401
 from .int_linear import QuantLinear  # noqa: F401
+from .int_llama_layer import QuantLlamaMLP  # noqa: F401
 
-__all__ = ["capi", "UniformAffineQuantizer", "QuantLinear"]
+__all__ = ["capi", "UniformAffineQuantizer", "QuantLinear", "QuantLlamaMLP"]

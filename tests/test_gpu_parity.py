@@ -496,3 +496,39 @@ def test_gemm_every_decomposition_vs_exact(capi, M, N, K, xb):
     if M >= 2048:
         # several passes over whole tiles: no split-K atomics, the same bits every time
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+def test_quant_llama_mlp_fused_chain_matches_module_composition(capi):
+    """QuantLlamaMLP (one gate_up GEMM + fused SiLU*up+quantise + down GEMM) against the same block composed of three
+    QuantLinear modules, which are pinned to the reference's golden outputs elsewhere."""
+    import types
+    from flexq_b200 import QuantLlamaMLP, model_pack
+    torch.manual_seed(21)
+    hid, inter = 1024, 2816
+
+    class Org(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj = torch.nn.Linear(hid, inter, bias=False)
+            self.up_proj = torch.nn.Linear(hid, inter, bias=False)
+            self.down_proj = torch.nn.Linear(inter, hid, bias=False)
+
+    org = Org().half().cuda()
+    args = types.SimpleNamespace(weight_quant_params=model_pack.default_quant_params(6, True),
+                                 act_quant_params=model_pack.default_quant_params(6, False),
+                                 act_down_proj_quant_params=model_pack.default_quant_params(8, False), flex_linear_quant=True)
+    mlp = QuantLlamaMLP(org, hid, inter, "silu", args)
+    mlp.set_quant_state(True, True)
+    assert mlp.down_proj.act_quantizer.n_bits == 8 and mlp.gate_proj.act_quantizer.n_bits == 6
+    for shape in ((1, 7, hid), (40, hid)):
+        x = torch.randn(*shape, device="cuda").half()
+        y, h = mlp(x)
+        h_ref = torch.nn.functional.silu(mlp.gate_proj(x)) * mlp.up_proj(x)          # module composition (reference forward)
+        y_ref = mlp.down_proj(h_ref)
+        assert y.shape == y_ref.shape and h.shape == h_ref.shape
+        assert torch.allclose(h.float(), h_ref.float(), rtol=4e-3, atol=4e-3)          # one rounding vs torch's two in fp16
+        rms = ((y.float() - y_ref.float()).pow(2).mean().sqrt() / y_ref.float().pow(2).mean().sqrt()).item()
+        assert rms <= 5e-3, rms                                                         # A8 requantisation of a slightly different h
+    mlp.set_quant_state(False, False)                                                   # not kernel-backed -> plain composition
+    y0, _ = mlp(x)
+    assert torch.allclose(y0.float(), org.down_proj(torch.nn.functional.silu(org.gate_proj(x)) * org.up_proj(x)).float(), rtol=1e-2, atol=1e-2)

@@ -204,3 +204,32 @@ def test_model_pack_driver_structure_and_packed_shards_cpu():
         model_pack.shard_packed(e, "column", 0, 8)          # 512 / 8 is not a whole tile
     with pytest.raises(ValueError):
         model_pack.shard_packed(e, "row", 0, 2)             # 3 groups do not split in 2
+
+
+def test_quant_llama_mlp_mirror_constructor_cpu():
+    """QuantLlamaMLP keeps the reference's constructor, sub-module names and bit policy (int_llama_layer.py:16-50)."""
+    import types
+    from flexq_b200 import QuantLinear, QuantLlamaMLP, model_pack
+
+    class Org(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj, self.up_proj, self.down_proj = nn.Linear(256, 512, bias=False), nn.Linear(256, 512, bias=False), nn.Linear(512, 256, bias=False)
+
+    def mk(flex):
+        return types.SimpleNamespace(weight_quant_params=model_pack.default_quant_params(6, True),
+                                     act_quant_params=model_pack.default_quant_params(6, False),
+                                     act_down_proj_quant_params=model_pack.default_quant_params(8, False), flex_linear_quant=flex)
+
+    mlp = QuantLlamaMLP(Org(), 256, 512, "silu", mk(True))
+    assert all(isinstance(m, QuantLinear) for m in (mlp.gate_proj, mlp.up_proj, mlp.down_proj))
+    assert mlp.down_proj.act_quantizer.n_bits == 8 and mlp.up_proj.act_quantizer.n_bits == 6
+    assert QuantLlamaMLP(Org(), 256, 512, "silu", mk(False)).down_proj.act_quantizer.n_bits == 6
+    mlp.set_quant_state(True, True)
+    assert mlp.gate_proj.use_weight_quant and mlp.down_proj.use_act_quant
+    from flexq_b200 import capi
+    with pytest.raises(capi.FlexQError):                  # real-quant path has no CPU fallback
+        mlp(torch.randn(4, 256))
+    mlp.set_quant_state(False, False)                     # quantisation off: plain modules, runs anywhere
+    y, h = mlp(torch.randn(4, 256))
+    assert y.shape == (4, 256) and h.shape == (4, 512)
