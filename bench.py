@@ -242,10 +242,11 @@ def main():
     ar_mode = "nccl"
     want_peer = os.environ.get("FLEXQ_BENCH_AR", "peer") == "peer"
     ar_chunks = int(os.environ.get("FLEXQ_BENCH_AR_CHUNKS", "2" if world >= 8 else "1"))
+    ar_reserve = int(os.environ.get("FLEXQ_BENCH_AR_RESERVE", "8"))
     if world > 1 and want_peer:
         try:
             for lin in layers:
-                lin.enable_peer_allreduce(M_TOKENS, chunks=ar_chunks, use_multicast=(world == 8), sm_reserve=8)
+                lin.enable_peer_allreduce(M_TOKENS, chunks=ar_chunks, use_multicast=(world == 8), sm_reserve=ar_reserve)
             ar_mode = "peer"
         except Exception as e:                       # noqa: BLE001
             for lin in layers:
