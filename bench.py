@@ -50,15 +50,19 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  The sampler process is started early (its
+    start-up takes longer than a short timed region); only samples stamped between begin() and end() are reported.  If the
+    region was too short to catch two samples, `stop(extend)` keeps the same kernels running for a fraction of a second
+    while sampling, so that the reported clocks are always clocks under this load."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.rows, self.proc, self.thread = [], None, None
+        self.t0, self.t1 = None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -67,22 +71,41 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
+
+    def _window(self):
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else time.monotonic()
+        return [r for t, r in self.rows if t0 <= t <= t1 + 0.02 and r and r[0].isdigit()]
+
+    def stop(self, extend=None):
         if self.proc is None:
             return None
+        rows = self._window()
+        if len(rows) < 2 and extend is not None:
+            self.t0 = time.monotonic()
+            while time.monotonic() - self.t0 < 0.6:
+                extend()
+            torch.cuda.synchronize()
+            self.t1 = time.monotonic()
+            rows = self._window()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        sm = sorted(int(r[0]) for r in rows)
         if not sm:
             return None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
+        mx = max(int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit())
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
 
 
@@ -215,6 +238,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     capi.load()
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs a moment before its first sample
 
     # ---- build the (sharded) layers: synthetic random-init weights, packed offline on the GPU
     torch.manual_seed(1234)
@@ -316,7 +340,8 @@ def main():
             ms = float(t.item())
         return ms / steps
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.begin()
     ms_step = timed(step_device, args.steps, args.warmup)
     ms_e2e = timed_e2e(max(5, args.steps // 2), 3)
 
@@ -333,7 +358,9 @@ def main():
                 capi.gemm_w6ax(xq, sx, lin.w6, lin.w_scale, lin.N, gws, o)
 
         ms_gemm = timed(gemm_only, args.steps, 3)
-        clocks = sampler.stop() if sampler else None
+        if sampler:
+            sampler.end()
+        clocks = sampler.stop(extend=step_device if world == 1 else None) if sampler else None
         _, bf16_tf, src = peaks()
         peak = 2.0 * bf16_tf                       # kind::i8 issues at twice the bf16 rate on sm_100
         achieved = total_ops / world / (ms_gemm * 1e-3) / 1e12
