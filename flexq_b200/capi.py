@@ -34,6 +34,7 @@ _SIGNATURES = {
     "flexq_bit_packing_i32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "flexq_bit_packing_f16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "flexq_quant_act": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "flexq_quant_act_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "flexq_pack_w6_i32": (_i, [_vp, _vp, _i, _i, _vp]),
     "flexq_pack_w6_i8": (_i, [_vp, _vp, _i, _i, _vp]),
     "flexq_quant_pack_w6_f16": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
@@ -125,9 +126,15 @@ def bit_packing_f16(x: torch.Tensor, bits: int):
 
 
 def quant_act(x: torch.Tensor, bits: int, mode: int = ROUND_CUDA):
+    """fp16 activations -> int8 containers + fp32 scales (mode selects the reference behaviour); fp32 activations
+    always take the python quantiser's fp32 arithmetic (flexq_quant_act_f32)."""
     M, K = x.shape
     xq = torch.empty(M, K, dtype=torch.int8, device=x.device)
     sx = torch.empty(K // GROUP, ceil4(M), dtype=torch.float32, device=x.device)
+    if x.dtype == torch.float32:
+        check(load().flexq_quant_act_f32(_ptr(x), _ptr(xq), _ptr(sx), M, K, bits, _stream()), "flexq_quant_act_f32")
+        return xq, sx
+    assert x.dtype == torch.float16, "flexq_quant_act takes fp16 or fp32 activations"
     check(load().flexq_quant_act(_ptr(x), _ptr(xq), _ptr(sx), M, K, bits, mode, _stream()), "flexq_quant_act")
     return xq, sx
 

@@ -453,6 +453,53 @@ int quant_act_native(const __half* x, int8_t* xq, float* sx, int M, int K, int b
     return (int)cudaLaunchKernelEx(&cfg, quant_act_native_kernel<FLEXQ_ROUND_CUDA, 1>, xv, xq, sx, M, K, ldsx, bits);
 }
 
+// fp32 activations, UniformAffineQuantizer arithmetic evaluated in fp32 exactly as torch does for float tensors
+// (/root/reference/algorithm/flexq_quantize/quantizer.py:144-155 scale = absmax / qmax clamped to [1e-5, 1e4];
+// :112-116 x_int = clamp(round_half_even(x / scale), qmin, qmax)).  This is the reference's CPU-runnable path
+// (BASELINE.json configs[0]); sx receives the fp32 scale itself, which the GEMM applies unrounded.
+__global__ void __launch_bounds__(256) quant_act_f32_kernel(const float4* __restrict__ x, int8_t* __restrict__ xq, float* __restrict__ sx,
+                                                            int M, int K, int ldsx, int bits) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int m = blockIdx.x;
+    const int lane16 = threadIdx.x & 15;
+    const int nvec = K >> 3;                                                // 8-float vectors per row
+    const int v = blockIdx.y * 256 + threadIdx.x;
+    if (v >= nvec) return;                                                  // whole 16-lane groups leave together
+    if (m >= M) {
+        if (lane16 == 0) sx[(size_t)(v >> 4) * ldsx + m] = 0.f;
+        return;
+    }
+    const float4* src = x + ((size_t)m * nvec + v) * 2;
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    const float xf[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(xf[i]));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const int hi = (1 << (bits - 1)) - 1, lo = -(1 << (bits - 1));
+    const float s = fminf(fmaxf(__fdiv_rn(amax, (float)hi), 1e-5f), 1e4f);
+    uint32_t w[2] = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float q = fminf(fmaxf(rintf(__fdiv_rn(xf[i], s)), (float)lo), (float)hi);
+        w[i >> 2] |= (uint32_t)((int)q & 0xFF) << (8 * (i & 3));
+    }
+    *reinterpret_cast<uint2*>(xq + (size_t)m * K + (size_t)v * 8) = make_uint2(w[0], w[1]);
+    if (lane16 == 0) sx[(size_t)(v >> 4) * ldsx + m] = s;
+}
+
+int quant_act_f32(const float* x, int8_t* xq, float* sx, int M, int K, int bits, cudaStream_t stream) {
+    if (!x || !xq || !sx) return FLEXQ_ERR_NULL;
+    if (M <= 0 || K < kGroup || K % kGroup) return FLEXQ_ERR_BAD_SHAPE;
+    if (bits != 6 && bits != 8) return FLEXQ_ERR_BAD_BITS;
+    const int ldsx = ceil4(M);
+    const int nvec = K / 8;
+    return launch_pdl(quant_act_f32_kernel, dim3(ldsx, (nvec + 255) / 256), 256, stream, reinterpret_cast<const float4*>(x), xq, sx, M, K,
+                      ldsx, bits);
+}
+
 int quant_act_planes(const __half* x, uint32_t* planes, __half* xs, int M, int K, int bits, cudaStream_t stream) {
     if (!x || !planes || !xs) return FLEXQ_ERR_NULL;
     if (M <= 0 || K < kGroup || K % kGroup || (M > 8 && M % 8)) return FLEXQ_ERR_BAD_SHAPE;

@@ -190,6 +190,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// K-major operand without swizzle: 8-row x 16-byte core matrices (128 contiguous bytes each); `lbo` = byte
+// distance between the core matrices of one 8-row group along K, `sbo` = between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+// same instruction shape with both operands unsigned 8-bit (format 0 @bit7 and @bit10)
+__host__ __device__ constexpr uint32_t umma_idesc_u8(int m, int n) {
+    return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 // Instruction descriptor, kind::i8: C=S32 (2 @bit4), A=B=signed int8 (1 @bit7, 1 @bit10),
 // both K-major, N>>3 @bit17, M>>4 @bit24  (cute InstrDescriptor).
 __host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
@@ -264,6 +273,13 @@ template <int kRegs>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

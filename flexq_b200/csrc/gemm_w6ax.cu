@@ -53,9 +53,25 @@ struct GemmParams {
         }                                                                                    \
     } while (0)
 
+// Accumulator seeding by the tensor core itself ("bias MMA"): the first MMA of every k-group is an
+// unsigned 255 x 255, K = 32 product of two constant operands, i.e. it overwrites the accumulator with
+// kBiasB = 32*255*255 = 2080800 >= max(-4S) = 128*127*128, and the four weight MMAs accumulate on top.  The
+// accumulator then holds the non-negative integer B + 4S < 2^23, whose bit pattern *is* the fp32 subnormal
+// (B + 4S) * 2^-149: the epilogue feeds it to an FMA unconverted (no per-element integer op at all) and
+// carries the power-of-two factors in its scale constants.  One more MMA per group on a tensor pipe that
+// has headroom, against one issue slot per output element per group saved.
+#ifndef FLEXQ_BIASMMA
+#define FLEXQ_BIASMMA 1
+#endif
+constexpr uint32_t kBiasB = 32u * 255u * 255u;
+
 template <int M_TILE, int GP>
 struct Cfg {
-    static constexpr int SMEM_BUDGET = 222 * 1024;                 // of the 227 KB a CTA may use
+    static constexpr bool BIAS = (FLEXQ_BIASMMA != 0) && (M_TILE >= 128);
+    // constant 0xFF operand region of the bias MMA: K-major, no swizzle, 8-row x 16-byte core matrices, two per
+    // 8-row group (K = 32 bytes); shared by both operands (every byte is the same)
+    static constexpr int ONES_BYTES = BIAS ? ((M_TILE > 128 ? M_TILE : 128) / 8) * 256 : 0;
+    static constexpr int SMEM_BUDGET = 222 * 1024 - ONES_BYTES;    // of the 227 KB a CTA may use
     // ---- TMEM columns: NAB accumulator step-buffers (GP groups x M_TILE) + NAT weight stages (GP x 32)
     static constexpr int ACC_COLS = GP * M_TILE;
     static constexpr int A_COLS = GP * 32;
@@ -86,7 +102,8 @@ struct Cfg {
     static constexpr int NDONE = 16;                               // "MMAs of step i retired" ring (> NAB, NAT, NX)
     static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
-    static constexpr int SMEM_BYTES = OFF_MISC + 16 + 1024;        // + alignment slack
+    static constexpr int OFF_ONES = (OFF_MISC + 16 + 127) / 128 * 128;
+    static constexpr int SMEM_BYTES = OFF_ONES + ONES_BYTES + 1024; // + alignment slack
     // epilogue warpgroups.  Measured on B200 (70B shapes, M >= 2048): 3 warpgroups of 64 columns (12 warps, 128 regs)
     // beat 2 x 96 columns (8 warps, 200 regs) by 3-8 % on the 192-token tile -- one more warp per scheduler to
     // cover FFMA2 dependencies; 4 x 48 columns are 4 % slower again (per-warp step overhead).  The 128-token
@@ -122,6 +139,13 @@ struct Cfg {
 #define FLEXQ_REARM 0
 #endif
 constexpr bool kRearm = FLEXQ_REARM != 0;
+#ifndef FLEXQ_ISSUER_WAITS_SCALES
+#define FLEXQ_ISSUER_WAITS_SCALES 1
+#endif
+constexpr bool kIssuerWaitsScales = FLEXQ_ISSUER_WAITS_SCALES != 0;
+#ifndef FLEXQ_EPI_PREFETCH
+#define FLEXQ_EPI_PREFETCH 1
+#endif
 
 // owner(u) = the CTA whose unit range [floor(c*U/P), floor((c+1)*U/P)) contains u
 __device__ __forceinline__ int unit_owner(int u, int U, int P) {
@@ -197,6 +221,11 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         prefetch_tensormap(&tmap_sw);
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(&misc[0]));
+    if constexpr (C::BIAS) {   // constant operand of the bias MMA, read through the async proxy
+        for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += C::THREADS)
+            reinterpret_cast<uint4*>(smem + C::OFF_ONES)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        fence_proxy_async_smem();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -283,7 +312,14 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     } else if (warp == 1 || warp == 2) {
         // ===================== MMA issuers (steps alternate between the two warps) =====================
         reg_dealloc<32>();
-        if (lane == 0) {
+        // The whole warp walks the loop converged and one elected lane issues: every MMA operand then derives from
+        // warp-uniform values (uniform registers), where a lane-0 branch made ptxas wrap each tcgen05.mma in an
+        // elect / broadcast / retry loop (~12 instructions and ~80 cycles per MMA).
+        const int my_parity = __shfl_sync(0xffffffffu, warp, 0) - 1;
+        const uint32_t tmem_base = __shfl_sync(0xffffffffu, misc[0], 0);
+        const uint32_t smem_base_u = __shfl_sync(0xffffffffu, smem_base, 0);
+        const bool leader = elect_one();
+        {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
             int it = 0;
             for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
@@ -291,12 +327,15 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int nt = u / G, g0 = u - nt * G;
                 const int g1 = min(G, g0 + (u_end - u));
                 for (int g = g0; g < g1; g += GP, it++) {
-                    if ((it & 1) != (warp - 1)) continue;
+                    if ((it & 1) != my_parity) continue;
                     const int ng = min(GP, g1 - g);
                     const int ab = it % C::NAB, st = it % C::NAT, sx_ = it % C::NX;
                     // the barrier expected to complete last is waited on last (an already-complete wait
                     // still costs ~200 cycles): accumulator hand-back when tensor-bound, weights when HBM-bound
                     mbar_wait(bar_x_full(sx_), (it / C::NX) & 1);
+                    // the scale block of this step: waited for here by one warp so that the epilogue warps need only the
+                    // "MMAs retired" barrier (which then implies it); it lands long before the accumulators come back
+                    if (kIssuerWaitsScales && !DUMP) mbar_wait(bar_s_full(it % C::NS), (it / C::NS) & 1);
                     if (GP == 1) {
                         mbar_wait(bar_a_full(st), (it / C::NAT) & 1);
                         mbar_wait(bar_acc_empty(ab), (it / C::NAB) & 1);   // handed back by the epilogue
@@ -304,22 +343,29 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         mbar_wait(bar_acc_empty(ab), (it / C::NAB) & 1);
                         mbar_wait(bar_a_full(st), (it / C::NAT) & 1);
                     }
-                    FQ_TRACE(it, 4);
+                    if (leader) FQ_TRACE(it, 4);
                     tc_fence_after();
                     // descriptor of the stage base once; per MMA only the 16-byte-unit address field advances
-                    const uint64_t b_desc0 = umma_desc_sw128(smem_base + C::OFF_X + sx_ * C::X_BYTES);
+                    const uint64_t b_desc0 = umma_desc_sw128(smem_base_u + C::OFF_X + sx_ * C::X_BYTES);
                     const uint32_t d_tmem = tmem_base + ab * C::ACC_COLS;
                     const uint32_t a_tmem = tmem_base + C::A_COL0 + st * C::A_COLS;
+                    if (leader) {
 #pragma unroll
-                    for (int j = 0; j < GP; j++) {
-                        if (j >= ng) break;
+                        for (int j = 0; j < GP; j++) {
+                            if (j >= ng) break;
+                            if constexpr (C::BIAS) {   // accumulator := 32 * 255 * 255 (unsigned x unsigned, constant operands)
+                                const uint64_t ones = umma_desc_nosw(smem_base_u + C::OFF_ONES, 128, 256);
+                                umma_i8(d_tmem + j * M_TILE, ones, ones, umma_idesc_u8(kTileN, M_TILE), 0u);
+                            }
 #pragma unroll
-                        for (int k = 0; k < 4; k++)
-                            umma_i8_ts(d_tmem + j * M_TILE, a_tmem + j * 32 + 8 * k,
-                                       b_desc0 + (uint64_t)((j * (M_TILE * 128) + 32 * k) >> 4), idesc, (kRearm || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < 4; k++)
+                                umma_i8_ts(d_tmem + j * M_TILE, a_tmem + j * 32 + 8 * k,
+                                           b_desc0 + (uint64_t)((j * (M_TILE * 128) + 32 * k) >> 4), idesc, (kRearm || C::BIAS || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(bar0 + 8u * (2 * C::NW + 2 * C::NS + C::NAT + C::NX + C::NAB + (it % C::NDONE)));
+                        FQ_TRACE(it, 5);
                     }
-                    umma_commit(bar_done(it));
-                    FQ_TRACE(it, 5);
+                    __syncwarp();
                 }
                 u += g1 - g0;
             }
@@ -376,6 +422,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         constexpr int CPT = C::CPT, CH = C::CH;
         constexpr uint32_t kMagicI = 0x4B400000u;
         constexpr float kMagicF = 12582912.f;
+        constexpr float kOutScale = C::BIAS ? 0x1p47f : 1.f;   // see the scale constants below
         const int e = threadIdx.x - 256;
         const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
         const int wg_id = e >> 7;                        // which CPT-column slice of the token tile
@@ -409,6 +456,13 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t bar_s_empty0 = bar_s_full0 + 8u * C::NS;
         const uint32_t bar_acc_empty0 = bar_s_full0 + 8u * (2 * C::NS + C::NAT + C::NX);
         const uint32_t bar_done0 = bar_acc_empty0 + 8u * C::NAB;
+        // Cross-step prefetch (1 group per step, even chunk count): all epilogue warps reach the end of a step together,
+        // so the barrier wait + first TMEM load of the next step would be a bubble nothing fills.  Instead the last
+        // chunk of a step probes the next step's "MMAs retired" barrier (normally long complete) and issues that
+        // step's first load before doing its own math; `pre` says the load is already in flight.
+        constexpr bool PREFETCH = (FLEXQ_EPI_PREFETCH != 0) && GP == 1 && ((CPT / CH) % 2 == 0) && !kRearm;
+        bool pre = false;
+        const int n_steps = PREFETCH ? ((p.m_tiles - cta_r + p.R - 1) / p.R) * (u_end - u_begin) : 0;
         for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
             for (int u = u_begin; u < u_end;) {
             const int nt = u / G, g0 = u - nt * G;
@@ -422,25 +476,28 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int ng = min(GP, g1 - g);
                 // ring positions are carried, not derived from `it`: no div/mod or address rebuild per step
                 const uint32_t sblk = s_base + (uint32_t)ss * C::S_BYTES;
-                if (!DUMP) mbar_wait(bar_s_full0 + 8u * ss, s_par);
-                mbar_wait(bar_done0 + 8u * dn, dn_par);
+                if (!DUMP && !kIssuerWaitsScales) mbar_wait(bar_s_full0 + 8u * ss, s_par);
+                if (!PREFETCH || !pre) {
+                    mbar_wait(bar_done0 + 8u * dn, dn_par);
+                    tc_fence_after();
+                }
                 if (e == 0) FQ_TRACE(it, 6);
-                tc_fence_after();
                 // TMEM drain, software pipelined: the load of chunk c+1 is in flight while chunk c is
                 // dequantised, and the buffer goes back to the MMA issuers as soon as its last chunk has
                 // been read and re-armed -- before that chunk's math.
                 constexpr int NCH = CPT / CH;
                 uint32_t v[2][CH];
-                auto ld_chunk = [&](int j, int c, uint32_t* dst) {
+                auto ld_chunk_of = [&](int buf, int j, int c, uint32_t* dst) {
 #ifdef FLEXQ_EXP_NOLD
                     for (int q = 0; q < CH; q++) dst[q] = (uint32_t)(j + c + q + it);   // experiment: no TMEM traffic
                     return;
 #endif
-                    const uint32_t ta = t_lane + ab * C::ACC_COLS + j * M_TILE + c * CH;
+                    const uint32_t ta = t_lane + buf * C::ACC_COLS + j * M_TILE + c * CH;
                     if constexpr (CH == 8) tmem_ld8(ta, dst);
                     else if constexpr (CH == 16) tmem_ld16(ta, dst);
                     else tmem_ld32(ta, dst);
                 };
+                auto ld_chunk = [&](int j, int c, uint32_t* dst) { ld_chunk_of(ab, j, c, dst); };
                 auto rearm_chunk = [&](int j, int c) {
                     const uint32_t ta = t_lane + ab * C::ACC_COLS + j * M_TILE + c * CH;
                     if constexpr (CH == 8) tmem_st8_same(ta, kMagicI);
@@ -455,7 +512,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_arrive(bar_acc_empty0 + 8u * ab);
                 if (false)
 #endif
-                ld_chunk(0, 0, v[0]);
+                if (!PREFETCH || !pre) ld_chunk(0, 0, v[0]);
+                pre = false;
 #pragma unroll
                 for (int j = 0; j < GP; j++) {           // unrolled: register double-buffer indices stay static
                     if (j >= ng) break;
@@ -465,9 +523,19 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     float2 sw2 = make_float2(0.f, 0.f), bias2 = make_float2(0.f, 0.f);
                     const uint32_t sxs = sblk + (uint32_t)(j * M_TILE + col0) * 4u;
                     if (!DUMP) {
-                        const float swv = n_ok ? 0.25f * __half2float(__ushort_as_half(lds_u16(sblk + C::SX_BYTES + (uint32_t)(j * kTileN + r) * 2u))) : 0.f;   // operands hold 4*w
-                        sw2 = make_float2(swv, swv);
-                        bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
+                        const float swh = n_ok ? __half2float(__ushort_as_half(lds_u16(sblk + C::SX_BYTES + (uint32_t)(j * kTileN + r) * 2u))) : 0.f;
+                        if constexpr (C::BIAS) {
+                            // accumulator bits = the subnormal (B + 4S) * 2^-149:  t = fma(v, sw * 2^100, -B * sw * 2^-49) = 4S * sw * 2^-49;
+                            // the tile's fp32 sums therefore carry a factor 2^-47 (operands hold 4*w) that the store removes
+                            const float c1 = swh * 0x1p100f;
+                            const float c2 = -(float)kBiasB * (swh * 0x1p-49f);
+                            sw2 = make_float2(c1, c1);
+                            bias2 = make_float2(c2, c2);
+                        } else {
+                            const float swv = 0.25f * swh;   // operands hold 4*w
+                            sw2 = make_float2(swv, swv);
+                            bias2 = make_float2(-kMagicF * swv, -kMagicF * swv);
+                        }
                     }
 #pragma unroll
                     for (int c = 0; c < NCH; c++) {
@@ -485,13 +553,23 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             if constexpr (kRearm) tmem_wait_st();    // every chunk read (and re-armed):
                             tc_fence_before();                       // hand the buffer back before the last math
                             mbar_arrive(bar_acc_empty0 + 8u * ab);
+                            if constexpr (PREFETCH) {
+                                if (it + 1 < n_steps) {
+                                    const int dn1 = (dn + 1 == C::NDONE) ? 0 : dn + 1;
+                                    pre = mbar_try_wait(bar_done0 + 8u * dn1, dn1 == 0 ? dn_par ^ 1u : dn_par);
+                                    if (pre) {
+                                        tc_fence_after();
+                                        ld_chunk_of((ab + 1 == C::NAB) ? 0 : ab + 1, 0, 0, nxt);
+                                    }
+                                }
+                            }
                         }
                         if constexpr (DUMP) {
                             if (n_ok) {
 #pragma unroll
                                 for (int q = 0; q < CH; q++) {
                                     const int m = mbase + c * CH + q;
-                                    if (m < p.M) p.S[((size_t)m * p.N + n) * G + g + j] = ((int32_t)(kRearm ? cur[q] - kMagicI : cur[q])) >> 2;
+                                    if (m < p.M) p.S[((size_t)m * p.N + n) * G + g + j] = ((int32_t)(C::BIAS ? cur[q] - kBiasB : kRearm ? cur[q] - kMagicI : cur[q])) >> 2;
                                 }
                             }
                         } else {
@@ -512,8 +590,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                 a1.y = fmaf(fmaf(__uint_as_float(cur[q + 3] + kAdd), sw2.x, bias2.x), s4.w, a1.y);
 #else
                                 constexpr int L = C::MAGIC_LOPS;
-                                const float2 t0 = __ffma2_rn(make_float2(magic_f32<kRearm, (L > 0)>(cur[q + 0]), magic_f32<kRearm, (L > 2)>(cur[q + 1])), sw2, bias2);
-                                const float2 t1 = __ffma2_rn(make_float2(magic_f32<kRearm, (L > 1)>(cur[q + 2]), magic_f32<kRearm, (L > 3)>(cur[q + 3])), sw2, bias2);
+                                constexpr bool RAW = kRearm || C::BIAS;      // accumulator bits are already the float to scale
+                                const float2 t0 = __ffma2_rn(make_float2(magic_f32<RAW, (L > 0)>(cur[q + 0]), magic_f32<RAW, (L > 2)>(cur[q + 1])), sw2, bias2);
+                                const float2 t1 = __ffma2_rn(make_float2(magic_f32<RAW, (L > 1)>(cur[q + 2]), magic_f32<RAW, (L > 3)>(cur[q + 3])), sw2, bias2);
                                 acc[(c * CH + q) / 2] = __ffma2_rn(t0, make_float2(s4.x, s4.y), acc[(c * CH + q) / 2]);
                                 acc[(c * CH + q) / 2 + 1] = __ffma2_rn(t1, make_float2(s4.z, s4.w), acc[(c * CH + q) / 2 + 1]);
 #endif
@@ -535,7 +614,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < CPT; j++) {
                             const int m = mbase + j;
-                            const float a = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
+                            const float a = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
                             if (m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n, __half_as_ushort(__float2half_rn(a)));   // streaming: do not displace X/W in L2
                         }
                     }
@@ -562,7 +641,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         for (int j = 0; j < CPT; j++) {
                             __stcg(sl + j * kTileN, 0.f);
                             const int m = mbase + j;
-                            const float vsum = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
+                            const float vsum = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
                             if (n_ok && m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n, __half_as_ushort(__float2half_rn(vsum)));
                         }
                         if (e == 0) p.cnt[slot] = 0;

@@ -105,12 +105,18 @@ class QuantLinear(nn.Module):
         w6, w_scale = self.pack_weights()
         lead = x.shape[:-1]
         x2 = x.reshape(-1, self.in_features)
-        if x2.dtype != torch.float16:
-            x2 = x2.half()
-        x2 = x2.contiguous()
         M = x2.shape[0]
-        ws = self._get_workspace(M, x2.device)
-        y = capi.linear_w6ax(x2, w6, w_scale, self.out_features, self.act_quantizer.n_bits, ws, self.act_round)
+        if x2.dtype == torch.float32:
+            # fp32 module (the reference's CPU-runnable configuration): the quantiser runs in fp32 arithmetic like
+            # torch does for float tensors, the integers and the fp32 activation scales are the reference's
+            xq, sx = capi.quant_act(x2.contiguous(), self.act_quantizer.n_bits)
+            y = capi.gemm_w6ax(xq, sx, w6, w_scale, self.out_features, self._get_workspace(M, x2.device))
+        else:
+            if x2.dtype != torch.float16:
+                x2 = x2.half()
+            x2 = x2.contiguous()
+            ws = self._get_workspace(M, x2.device)
+            y = capi.linear_w6ax(x2, w6, w_scale, self.out_features, self.act_quantizer.n_bits, ws, self.act_round)
         if self.bias is not None:
             y = y + self.bias.to(y.dtype)
         return y.reshape(*lead, self.out_features).to(x.dtype)

@@ -79,6 +79,12 @@ int flexq_bit_packing_f16(const void* x_half, int32_t* planes, void* x_scale_hal
 int flexq_quant_act(const void* x_half, int8_t* xq, float* sx, int M, int K, int bits, int mode,
                     void* stream);
 
+/* fp32 activations: the same quantiser evaluated in fp32 arithmetic, as UniformAffineQuantizer does for float
+ * tensors (quantizer.py:144-155 scale = absmax/qmax clamped to [1e-5,1e4]; :112-116 round half to even, clamp) --
+ * the reference's CPU-runnable path (QuantLinear on an fp32 module, int_linear.py:56-72).  sx receives the fp32
+ * scale unrounded.                                                                                              */
+int flexq_quant_act_f32(const float* x, int8_t* xq, float* sx, int M, int K, int bits, void* stream);
+
 /* ---- offline weight packer (north-star subsystem 1) --------------------------------------
  * ints [N][K] (two's complement in 6 bits, i.e. [-32,31]; int32 or int8 input) -> W6 tiles.
  * Caller of the int32 form today: engine/test_bgemm_kernel.cu:222-224 (flexq_bit_packing on W). */

@@ -216,6 +216,35 @@ def test_gemm_extreme_values(capi, oracle):
     assert np.array_equal(S, oracle.group_sums(xq.astype(np.int32), wq.astype(np.int32)))
 
 
+@pytest.mark.parametrize("M", [128, 192, 200])
+def test_gemm_extreme_values_prefill_tiles(capi, oracle, M):
+    """The 128/192-token tiles seed every accumulator with 32*255*255 through a constant unsigned MMA and read it back
+    as an fp32 subnormal: the most negative group sum (w = -32, x = +127: 4S = -2080768) must leave it positive, the
+    most positive one (w = -32, x = -128) must stay below 2^23 -- both the integers and the fp16 outputs are checked."""
+    N, K = 256, 384
+    xq = np.full((M, K), 127, dtype=np.int8)
+    xq[1::2] = -128
+    xq[:, 128:256] = np.random.default_rng(0).integers(-128, 128, size=(M, 128))
+    wq = np.full((N, K), -32, dtype=np.int8)
+    wq[::3] = 31
+    w6 = capi.pack_w6(torch.from_numpy(wq).cuda())
+    xd = torch.from_numpy(xq).cuda()
+    S = capi.gemm_w6ax_groupsums(xd, w6, N).cpu().numpy()
+    S_ref = oracle.group_sums(xq.astype(np.int32), wq.astype(np.int32))
+    assert np.array_equal(S, S_ref)
+    assert S_ref.min() == -32 * 127 * 128 and S_ref.max() == 32 * 128 * 128
+    rng = np.random.default_rng(1)
+    sx = (rng.random((M, K // 128)) * 1e-3 + 1e-5).astype(np.float16)
+    sw = (rng.random((K // 128, N)) * 1e-3 + 1e-5).astype(np.float16)
+    sw[0, :8] = np.float16(6e-8)                 # fp16 subnormal weight scales
+    sx[:4, 0] = np.float16(30.0)
+    out = capi.gemm_w6ax(xd, _sx_dev(capi, sx, M, K // 128), w6, torch.from_numpy(sw).cuda(), N, capi.new_workspace()).cpu().numpy()
+    # outputs span four orders of magnitude here: element-wise bound (one fp16 rounding = 4.9e-4 relative) instead
+    # of the max-abs / mean form of _check_close
+    ref = oracle.gemm_exact(S_ref, sx, sw).astype(np.float64)
+    assert np.all(np.abs(out.astype(np.float64) - ref) <= 1e-3 * np.abs(ref) + 1e-4 * np.abs(ref).mean())
+
+
 @pytest.mark.parametrize("M,N,K,xb", [(16, 4096, 4096, 6), (8, 1024, 2048, 8), (128, 1024, 1024, 6)])
 def test_linear_vs_fakequant(capi, oracle, M, N, K, xb):
     """Fused fp16 linear vs the reference's fake-quant path (oracle.fakequant_linear is pinned to
@@ -496,6 +525,49 @@ def test_gemm_every_decomposition_vs_exact(capi, M, N, K, xb):
     if M >= 2048:
         # several passes over whole tiles: no split-K atomics, the same bits every time
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
+def _exact_w6ax_chunked(capi, xq, sx, w6, wsc, N, n_chunk=2048):
+    """_exact_w6ax for BASELINE-size problems: float64 group sums one slab of output columns at a time."""
+    M, K = xq.shape
+    G = K // 128
+    wq = capi.w6_to_i8(w6, N, K)
+    xg = xq.double().view(M, G, 128)
+    sxd = sx[:, :M].double()
+    out = torch.empty(M, N, dtype=torch.float64, device=xq.device)
+    for n0 in range(0, N, n_chunk):
+        n1 = min(N, n0 + n_chunk)
+        S = torch.einsum("mgk,ngk->gmn", xg, wq[n0:n1].double().view(n1 - n0, G, 128))
+        out[:, n0:n1] = torch.einsum("gmn,gm,gn->mn", S, sxd, wsc[:, n0:n1].double())
+        del S
+    return out
+
+
+# the exact BASELINE.json shapes: configs[2] (70B linears, M = 2048, W6A6; down_proj also W6A8) and the per-rank
+# shapes of configs[4] at tp = 8 (column-parallel N/8, row-parallel K/8)
+C3_C5_SHAPES = [(2048, 8192, 8192, 6), (2048, 28672, 8192, 6), (2048, 8192, 28672, 6), (2048, 8192, 28672, 8),
+                (2048, 8192, 1024, 8), (2048, 3584, 8192, 8), (2048, 8192, 3584, 8), (2048, 1024, 8192, 8), (4096, 8192, 8192, 8)]
+
+
+@pytest.mark.parametrize("M,N,K,xb", C3_C5_SHAPES)
+def test_gemm_fp16_output_at_baseline_shapes(capi, M, N, K, xb):
+    dev = torch.device("cuda")
+    torch.manual_seed(N + K + xb)
+    w6, wsc = capi.quant_pack_w6((0.02 * torch.randn(N, K, device=dev)).half())
+    x = torch.randn(M, K, device=dev).half()
+    xq, sx = capi.quant_act(x, xb)
+    ws = capi.new_workspace()
+    out = capi.gemm_w6ax(xq, sx, w6, wsc, N, ws)
+    ref = _exact_w6ax_chunked(capi, xq, sx, w6, wsc, N)
+    err = (out.double() - ref).abs()
+    assert (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() <= RMS_REL_TOL
+    assert (err.max() / ref.abs().mean()).item() <= MAXABS_REL_TOL
+    assert not ws.any().item(), "split-K workspace not restored to zero"
+    # INT32 group sums of the same launch configuration against the float64 integer matmul (exact below 2^53)
+    if N * K <= 8192 * 8192:
+        S = capi.gemm_w6ax_groupsums(xq, w6, N)
+        wq = capi.w6_to_i8(w6, N, K)
+        assert torch.equal(S.long().sum(dim=2), (xq.double() @ wq.double().t()).round().long())
 
 
 def test_quant_llama_mlp_fused_chain_matches_module_composition(capi):
