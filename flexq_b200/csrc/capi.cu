@@ -6,6 +6,7 @@ namespace flexq {
 int quant_act_native(const __half*, int8_t*, float*, int, int, int, int, cudaStream_t);
 int quant_act_planes(const __half*, uint32_t*, __half*, int, int, int, cudaStream_t);
 int quant_act_f32(const float*, int8_t*, float*, int, int, int, cudaStream_t);
+int debug_schedule(int, int, int, int, int, int*, int, int*);
 template <typename T> int pack_w6(const T*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int quant_pack_w6(const T*, uint8_t*, __half*, int, int, cudaStream_t);
 int unpack_w6(const uint8_t*, int8_t*, int, int, cudaStream_t);
@@ -68,6 +69,10 @@ int flexq_bit_packing_f16(const void* x, int32_t* planes, void* xs, int M, int K
 
 int flexq_quant_act(const void* x, int8_t* xq, float* sx, int M, int K, int bits, int mode, void* stream) {
     return quant_act_native((const __half*)x, xq, sx, M, K, bits, mode, (cudaStream_t)stream);
+}
+
+int flexq_debug_schedule(int m_tiles, int n_tiles, int groups, int max_ctas, int cta, int* segments, int cap, int* n_ctas) {
+    return debug_schedule(m_tiles, n_tiles, groups, max_ctas, cta, segments, cap, n_ctas);
 }
 
 int flexq_quant_act_f32(const float* x, int8_t* xq, float* sx, int M, int K, int bits, void* stream) {

@@ -40,8 +40,9 @@ struct GemmParams {
     int M, N, K, G;
     int m_tiles, n_tiles;    // tile index = mt * n_tiles + nt: CTAs that run concurrently stream the same weight rows
                              // (one token tile each), so a weight row is fetched from HBM once and hit in L2 by the rest
-    int Pn, R;               // grid = Pn columns x R rows
-    int tile_gran;           // 1: columns own whole n-tiles (several passes over token tiles)
+    int P, Pn, R;            // P CTAs: R rows x Pn columns of regular CTAs + (P - R*Pn) spare ones (see Sched)
+    int Ureg;                // units [0, Ureg) of every token tile belong to the regular CTAs
+    int whole_rows;          // 1: more token tiles than CTAs, every CTA owns whole token tiles
     long long* trace;        // TRACE builds: [step][16] clock64 stamps of CTA 0
     int trace_units;
 };
@@ -144,12 +145,114 @@ constexpr bool kRearm = FLEXQ_REARM != 0;
 #endif
 constexpr bool kIssuerWaitsScales = FLEXQ_ISSUER_WAITS_SCALES != 0;
 #ifndef FLEXQ_EPI_PREFETCH
-#define FLEXQ_EPI_PREFETCH 1
+#define FLEXQ_EPI_PREFETCH 0
 #endif
 
 // owner(u) = the CTA whose unit range [floor(c*U/P), floor((c+1)*U/P)) contains u
-__device__ __forceinline__ int unit_owner(int u, int U, int P) {
+__host__ __device__ __forceinline__ int unit_owner(int u, int U, int P) {
     return (int)((((long long)u + 1) * P - 1) / U);
+}
+
+// Work decomposition.  A unit is (token tile mt, n-tile nt, k-group g); within a token tile the units are ordered
+// u = nt * G + g (Umt = n_tiles * G of them).
+//   * R = m_tiles rows x Pn columns of "regular" CTAs: row r owns token tile r, the Pn columns split units [0, Ureg)
+//     of every token tile into the same contiguous ranges, so the CTAs of a column stream identical weight tiles at
+//     the same time (one HBM fetch, L2 hits for the other rows).
+//   * the P - R*Pn CTAs that do not fill another column ("spare") share units [Ureg, Umt) of all token tiles,
+//     linearised as (mt, u); Ureg is chosen so that every CTA gets the same number of units (+-1).
+//   * more token tiles than CTAs: every CTA owns whole token tiles mt = cta, cta + P, ...
+// Splits are at k-group granularity (stream-K): a tile cut by a range boundary is summed through the fp32 slot of
+// the CTA that owns the tile's first unit (each CTA owns the first unit of at most one cut tile).
+struct Sched {
+    int a, b;          // index range of this CTA
+    int L;             // indices per row of the index space
+    int mt0, mts;      // token tile of row i = mt0 + i * mts
+    int ub;            // unit of index 0 within a row
+};
+
+__host__ __device__ __forceinline__ Sched make_sched(const GemmParams& p, int cta) {
+    const int Umt = p.n_tiles * p.G;
+    Sched s;
+    if (p.whole_rows) {                      // m_tiles > P: whole token tiles, several passes
+        const int passes = (p.m_tiles - cta + p.P - 1) / p.P;
+        s.a = 0; s.b = passes * Umt; s.L = Umt; s.mt0 = cta; s.mts = p.P; s.ub = 0;
+    } else if (cta < p.R * p.Pn) {
+        const int j = cta % p.Pn;
+        s.a = (int)(((long long)j * p.Ureg) / p.Pn);
+        s.b = (int)(((long long)(j + 1) * p.Ureg) / p.Pn);
+        s.L = 0x40000000; s.mt0 = cta / p.Pn; s.mts = 0; s.ub = 0;
+    } else {
+        const int sp = cta - p.R * p.Pn, nsp = p.P - p.R * p.Pn;
+        const long long tot = (long long)p.R * (Umt - p.Ureg);
+        s.a = (int)((sp * tot) / nsp);
+        s.b = (int)(((sp + 1) * tot) / nsp);
+        s.L = Umt - p.Ureg; s.mt0 = 0; s.mts = 1; s.ub = p.Ureg;
+    }
+    return s;
+}
+
+// f(mt, nt, g0, g1) for every maximal run of k-groups [g0, g1) of one tile in this CTA's range, in order
+template <typename F>
+__host__ __device__ __forceinline__ void walk_segments(const Sched& s, int G, F&& f) {
+    for (int idx = s.a; idx < s.b;) {
+        const int row = idx / s.L;
+        const int rend = (long long)(row + 1) * s.L < (long long)s.b ? (row + 1) * s.L : s.b;
+        const int mt = s.mt0 + row * s.mts;
+        for (int u = s.ub + (idx - row * s.L), ue = u + (rend - idx); u < ue;) {
+            const int nt = u / G, g0 = u - nt * G;
+            const int g1 = g0 + (ue - u) < G ? g0 + (ue - u) : G;
+            f(mt, nt, g0, g1);
+            u += g1 - g0;
+        }
+        idx = rend;
+    }
+}
+
+// slot of the fp32 partial sums of tile (mt, nt): the CTA that owns the tile's first unit
+__host__ __device__ __forceinline__ int tile_slot(const GemmParams& p, int mt, int nt) {
+    const int u0 = nt * p.G;
+    if (u0 < p.Ureg) return mt * p.Pn + unit_owner(u0, p.Ureg, p.Pn);
+    const int Ls = p.n_tiles * p.G - p.Ureg;
+    const long long tot = (long long)p.R * Ls, i0 = (long long)mt * Ls + (u0 - p.Ureg);
+    const int nsp = p.P - p.R * p.Pn;
+    return p.R * p.Pn + (int)(((i0 + 1) * nsp - 1) / tot);
+}
+
+// host: fill the decomposition fields of p (n_tiles, m_tiles, G set) for at most max_ctas CTAs
+static void plan_ctas(GemmParams& p, int max_ctas) {
+    const long long Umt = (long long)p.n_tiles * p.G;
+    if (p.m_tiles > max_ctas) {
+        p.whole_rows = 1; p.P = max_ctas; p.R = max_ctas; p.Pn = 1; p.Ureg = (int)Umt;
+        return;
+    }
+    p.whole_rows = 0;
+    p.R = p.m_tiles;
+    p.Pn = max_ctas / p.R;
+    if (p.Pn > Umt) p.Pn = (int)Umt;                                      // at least one unit per CTA
+    int spare = p.Pn < Umt ? max_ctas - p.R * p.Pn : 0;
+    p.P = p.R * p.Pn + spare;
+    p.Ureg = spare ? (int)((Umt * p.R * p.Pn + p.P / 2) / p.P) : (int)Umt;
+    // every regular CTA and every spare CTA must own at least one unit
+    if (spare && (p.Ureg < p.Pn || (long long)p.R * (Umt - p.Ureg) < spare)) { p.P = p.R * p.Pn; p.Ureg = (int)Umt; }
+}
+
+// debug / test: the segments (mt, nt, g0, g1, slot) CTA `cta` walks for a problem of m_tiles x n_tiles x G units on at
+// most max_ctas CTAs; returns the number of segments (written up to cap), *n_ctas = CTAs launched
+int debug_schedule(int m_tiles, int n_tiles, int G, int max_ctas, int cta, int* out, int cap, int* n_ctas) {
+    GemmParams p{};
+    p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.G = G;
+    plan_ctas(p, max_ctas);
+    if (n_ctas) *n_ctas = p.P;
+    if (cta < 0 || cta >= p.P) return 0;
+    int n = 0;
+    walk_segments(make_sched(p, cta), G, [&](int mt, int nt, int g0, int g1) {
+        if (n < cap) {
+            out[5 * n] = mt; out[5 * n + 1] = nt; out[5 * n + 2] = g0; out[5 * n + 3] = g1;
+            out[5 * n + 4] = (g0 == 0 && g1 == G) ? -1 : tile_slot(p, mt, nt);
+        }
+        n++;
+    });
+    return n;
 }
 
 // int32 group sum 4S (|4S| <= 2^21) -> the float 12582912 + 4S, bit-wise: the low 23 bits of 4S with bit 22
@@ -184,15 +287,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     }
     const int G = p.G;
-    // CTA = (column j, row r): row r owns token tiles mt = r, r+R, ...; the Pn columns split the
-    // (n-tile, k-group) units of a token tile into the same contiguous ranges for every row, so
-    // the CTAs of a column stream identical weight tiles at the same time (one HBM fetch, L2 hits
-    // for the rest).  With a single pass the split is at group granularity (stream-K, partial tiles
-    // reduced through the scratch); with several passes it is at tile granularity (no partial tiles).
-    const int cta_j = blockIdx.x % p.Pn, cta_r = blockIdx.x / p.Pn;
+    const Sched sch = make_sched(p, blockIdx.x);
     const int Umt = p.n_tiles * G;
-    const int u_begin = p.tile_gran ? (int)(((long long)cta_j * p.n_tiles) / p.Pn) * G : (int)(((long long)cta_j * Umt) / p.Pn);
-    const int u_end = p.tile_gran ? (int)(((long long)(cta_j + 1) * p.n_tiles) / p.Pn) * G : (int)(((long long)(cta_j + 1) * Umt) / p.Pn);
 
     // full/empty rings.  One tcgen05.commit per step arrives on bar_done(step % NDONE); it frees the
     // activation stage and the TMEM weight stage of that step and publishes its accumulators.
@@ -249,10 +345,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             // re-streamed per token tile and should stay resident
             const uint64_t pol = (p.m_tiles == 1) ? l2_policy_evict_first() : l2_policy_evict_last();
             int it = 0;
-            for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
-            for (int u = u_begin; u < u_end;) {
-                const int nt = u / G, g0 = u - nt * G;
-                const int g1 = min(G, g0 + (u_end - u));
+            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
                 const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
                 for (int g = g0; g < g1; g += GP, it++) {
                     const int ng = min(GP, g1 - g);
@@ -270,7 +363,13 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                              (nt * G + g + j) * (kTileBytes / 128), bar_w_full(s), pol);
                     }
                 }
-                u += g1 - g0;
+            });
+        } else if (TRACE && lane == 1 && blockIdx.x == (p.trace_units >> 16)) {
+            // trace builds: an otherwise idle lane watches the "MMAs of step i retired" barriers (event 8)
+            const int n = min(sch.b - sch.a, p.trace_units & 0xFFFF);
+            for (int i = 0; i < n && GP == 1; i++) {
+                mbar_wait(bar_done(i), done_parity(i));
+                FQ_TRACE(i, 8);
             }
         }
         __syncwarp();
@@ -281,10 +380,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             asm volatile("griddepcontrol.wait;" ::: "memory");     // activations / scales come from earlier kernels
             const uint64_t pol_x = l2_policy_evict_last();          // every n-tile re-reads the activations: keep them in L2
             int it = 0;
-            for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
-            for (int u = u_begin; u < u_end;) {
-                const int nt = u / G, g0 = u - nt * G;
-                const int g1 = min(G, g0 + (u_end - u));
+            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
                 for (int g = g0; g < g1; g += GP, it++) {
                     {   // [ng][M_TILE][128 B] swizzle-128B tiles, one TMA per k-group; rows >= M are zero-filled
                         const int ng = min(GP, g1 - g);
@@ -305,8 +401,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         tma_load_2d(dst + C::SX_BYTES, &tmap_sw, nt * kTileN, g, bar_s_full(s));
                     }
                 }
-                u += g1 - g0;
-            }
+            });
         }
         __syncwarp();
     } else if (warp == 1 || warp == 2) {
@@ -322,10 +417,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
             int it = 0;
-            for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
-            for (int u = u_begin; u < u_end;) {
-                const int nt = u / G, g0 = u - nt * G;
-                const int g1 = min(G, g0 + (u_end - u));
+            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
                 for (int g = g0; g < g1; g += GP, it++) {
                     if ((it & 1) != my_parity) continue;
                     const int ng = min(GP, g1 - g);
@@ -353,6 +445,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < GP; j++) {
                             if (j >= ng) break;
+#ifdef FLEXQ_EXP_SKIPBIASMMA
+                            if (false)                 // experiment: cost of the fifth MMA (results invalid)
+#endif
                             if constexpr (C::BIAS) {   // accumulator := 32 * 255 * 255 (unsigned x unsigned, constant operands)
                                 const uint64_t ones = umma_desc_nosw(smem_base_u + C::OFF_ONES, 128, 256);
                                 umma_i8(d_tmem + j * M_TILE, ones, ones, umma_idesc_u8(kTileN, M_TILE), 0u);
@@ -367,8 +462,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                     __syncwarp();
                 }
-                u += g1 - g0;
-            }
+            });
         }
         __syncwarp();
     } else if (warp < 8) {
@@ -377,10 +471,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int r = threadIdx.x - 128;                 // weight row within the tile == TMEM lane
         const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + C::A_COL0;
         int it = 0;
-        for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
-            for (int u = u_begin; u < u_end;) {
-            const int nt = u / G, g0 = u - nt * G;
-            const int g1 = min(G, g0 + (u_end - u));
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             for (int g = g0; g < g1; g += GP, it++) {
                 const int ng = min(GP, g1 - g);
                 const int sw = it % C::NW, st = it % C::NAT;
@@ -410,8 +501,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 mbar_arrive(bar_a_full(st));
                 if (r == 0) FQ_TRACE(it, 3);
             }
-            u += g1 - g0;
-        }
+                    });
     } else {
         // ===================== epilogue =====================
         // The int32 group sum 4*S read back from TMEM is turned into the float (kMagicF + 4*S) bit-wise (magic_f32:
@@ -462,11 +552,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // step's first load before doing its own math; `pre` says the load is already in flight.
         constexpr bool PREFETCH = (FLEXQ_EPI_PREFETCH != 0) && GP == 1 && ((CPT / CH) % 2 == 0) && !kRearm;
         bool pre = false;
-        const int n_steps = PREFETCH ? ((p.m_tiles - cta_r + p.R - 1) / p.R) * (u_end - u_begin) : 0;
-        for (int mt = cta_r; mt < p.m_tiles; mt += p.R)
-            for (int u = u_begin; u < u_end;) {
-            const int nt = u / G, g0 = u - nt * G;
-            const int g1 = min(G, g0 + (u_end - u));
+        const int n_steps = sch.b - sch.a;
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             const int n = nt * kTileN + r;
             const int mbase = mt * M_TILE + col0;
             const bool n_ok = n < p.N;
@@ -579,7 +666,11 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #endif
 #pragma unroll
                             for (int q = 0; q < CH; q += 4) {
+#ifdef FLEXQ_EXP_NOSX
+                                const float4 s4 = make_float4(sw2.x, bias2.x, sw2.x, bias2.x);      // experiment: no shared-memory scale reads
+#else
                                 const float4 s4 = lds_f4(sxs + (uint32_t)(c * CH + q) * 4u);
+#endif
                                 constexpr uint32_t kAdd = kRearm ? 0u : kMagicI;   // int32 4S -> bits of the float (kMagicF + 4S)
 #ifdef FLEXQ_EXP_SCALAR
                                 float2& a0 = acc[(c * CH + q) / 2];
@@ -620,7 +711,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                 } else {
                     // partial tile: accumulate in the slot owned by the tile's first CTA
-                    const int slot = cta_r * p.Pn + unit_owner(nt * G, Umt, p.Pn);   // single pass: (row, first column of the tile) is unique
+                    const int slot = tile_slot(p, mt, nt);
                     float* sl = p.slots + (size_t)slot * kSlotFloats + (size_t)col0 * kTileN + r;
 #pragma unroll
                     for (int j = 0; j < CPT; j++) atomicAdd(sl + j * kTileN, (j & 1) ? acc[j / 2].y : acc[j / 2].x);
@@ -650,8 +741,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
             if (e == 0) FQ_TRACE(it - 1, 11);
-            u += g1 - g0;
-        }
+                    });
     }
 
     tc_fence_before();
@@ -776,21 +866,12 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
 
     p.n_tiles = ceil_div(p.N, kTileN);
     p.m_tiles = ceil_div(p.M, M_TILE);
-    {   // pick R rows x Pn columns minimising the per-CTA work (in k-group units); ties -> more rows (more sharing)
+    {
         int max_ctas = sms < kMaxCtas ? sms : kMaxCtas;
         if (g_sm_limit > 0 && g_sm_limit < max_ctas) max_ctas = g_sm_limit;
-        const long long Umt = (long long)p.n_tiles * p.G;
-        long long best = -1;
-        for (int R = 1; R <= p.m_tiles && R <= max_ctas; R++) {
-            long long Pn = max_ctas / R;
-            const int passes = ceil_div(p.m_tiles, R);
-            long long cost;
-            if (passes == 1) { if (Pn > Umt) Pn = Umt; cost = (Umt + Pn - 1) / Pn; }
-            else { if (Pn > p.n_tiles) Pn = p.n_tiles; cost = (long long)passes * ((p.n_tiles + Pn - 1) / Pn) * p.G; }
-            if (best < 0 || cost <= best) { best = cost; p.R = R; p.Pn = (int)Pn; p.tile_gran = passes > 1; }
-        }
+        plan_ctas(p, max_ctas);
     }
-    const int P = p.Pn * p.R;
+    const int P = p.P;
 
     static bool attr_set = false;
     if (!attr_set) {

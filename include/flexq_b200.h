@@ -118,6 +118,12 @@ int flexq_gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const 
 int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K,
                               void* stream);
 
+/* Debug / tests (host only, no device work): the work decomposition of the GEMM.  For a problem of m_tiles token
+ * tiles x n_tiles weight tiles x `groups` k-groups on at most max_ctas CTAs, writes the segments CTA `cta` walks as
+ * int[5] = {token tile, n-tile, first group, end group, fp32 slot or -1 when the CTA covers the whole tile} (up to
+ * `cap` of them), stores the number of CTAs launched in *n_ctas and returns the CTA's segment count.        */
+int flexq_debug_schedule(int m_tiles, int n_tiles, int groups, int max_ctas, int cta, int* segments, int cap, int* n_ctas);
+
 /* Debug only: the GEMM with clock64 stamps of CTA 0's pipeline events, trace[unit][16]
  * (M <= 16 runs the decode tile, otherwise the 256-token tile); used by tools/trace.py. */
 int flexq_debug_gemm_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale_half,

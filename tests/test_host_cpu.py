@@ -233,3 +233,44 @@ def test_quant_llama_mlp_mirror_constructor_cpu():
     mlp.set_quant_state(False, False)                     # quantisation off: plain modules, runs anywhere
     y, h = mlp(torch.randn(4, 256))
     assert y.shape == (4, 256) and h.shape == (4, 512)
+
+
+@pytest.mark.parametrize("m_tiles,n_tiles,G,max_ctas", [
+    (1, 64, 64, 148), (1, 224, 64, 148), (1, 2, 3, 148), (2, 32, 32, 148), (3, 7, 5, 148), (6, 64, 64, 148), (11, 224, 64, 148),
+    (11, 64, 64, 148), (11, 64, 224, 148), (22, 224, 64, 148), (22, 64, 8, 140), (75, 9, 4, 148), (148, 3, 2, 148),
+    (149, 3, 2, 148), (400, 5, 3, 148), (5, 1, 1, 148), (13, 28, 64, 147)])
+def test_gemm_work_decomposition_covers_every_unit_once(m_tiles, n_tiles, G, max_ctas):
+    """Host logic of the W6Ax GEMM's schedule (csrc/gemm_w6ax.cu Sched / plan_ctas), through the C ABI without a GPU:
+    every (token tile, n-tile, k-group) unit is owned by exactly one CTA, CTA loads are balanced to within a couple of units (when
+    token tiles do not outnumber CTAs), tiles cut by a range boundary use one fp32 slot that no other cut tile shares,
+    and each CTA owns at most one slot."""
+    import ctypes
+    from flexq_b200 import capi
+    lib = capi.load()
+    n_ctas = ctypes.c_int(0)
+    cap = 4096
+    buf = (ctypes.c_int * (5 * cap))()
+    lib.flexq_debug_schedule(m_tiles, n_tiles, G, max_ctas, 0, buf, cap, ctypes.byref(n_ctas))
+    P = n_ctas.value
+    assert 1 <= P <= max_ctas
+    owned = np.zeros((m_tiles, n_tiles, G), dtype=np.int32)
+    slot_of_tile, loads = {}, []
+    for cta in range(P):
+        n = lib.flexq_debug_schedule(m_tiles, n_tiles, G, max_ctas, cta, buf, cap, ctypes.byref(n_ctas))
+        assert 0 < n <= cap
+        seg = np.ctypeslib.as_array(buf)[:5 * n].reshape(n, 5).copy()
+        loads.append(int((seg[:, 3] - seg[:, 2]).sum()))
+        for mt, nt, g0, g1, slot in seg:
+            assert 0 <= g0 < g1 <= G
+            owned[mt, nt, g0:g1] += 1
+            if slot >= 0:
+                assert slot < P
+                assert slot_of_tile.setdefault((mt, nt), slot) == slot, "contributors of a cut tile disagree on its slot"
+            else:
+                assert g0 == 0 and g1 == G
+    assert (owned == 1).all()
+    slots = list(slot_of_tile.values())
+    assert len(slots) == len(set(slots)), "two cut tiles share an fp32 slot"
+    if m_tiles <= max_ctas:
+        # Ureg is rounded to a whole unit: the spare CTAs share that rounding error times the number of token tiles
+        assert max(loads) - min(loads) <= max(2, 0.02 * np.mean(loads) + m_tiles / 2), (min(loads), max(loads))

@@ -47,7 +47,7 @@ d_ = (w[:, 1] - w[:, 0]) / 1e3
 print("slowest CTAs", np.argsort(-d_)[:8], np.sort(-d_)[:8])
 t = full[:a.units * 16].reshape(a.units, 16)
 t0 = t[t > 0].min()
-names = ["Wissue", "Wfull", "Aempty", "Afull", "MMArdy", "MMAcmt", "ACCfull", "ACCfree", "EPIend", "Xissue", "FIXbeg", "FIXend", "END", "START"]
+names = ["Wissue", "Wfull", "Aempty", "Afull", "MMArdy", "MMAcmt", "ACCfull", "ACCfree", "MMAdone", "Xissue", "FIXbeg", "FIXend", "END", "START"]
 print("unit " + " ".join(f"{n:>8}" for n in names))
 for i in range(a.units):
     print(f"{i:4d} " + " ".join(f"{(t[i, e] - t0) if t[i, e] else -1:8d}" for e in range(14)))
