@@ -30,15 +30,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 M_TOKENS = 2048
-# (name, N, K, tensor-parallel mode, activation bits)
-LAYERS = [("attn_o_8192x8192", 8192, 8192, "row", 6),
-          ("mlp_gate_28672x8192", 28672, 8192, "column", 6),
-          ("mlp_down_8192x28672", 8192, 28672, "row", 6)]
-# dram__bytes_read.sum + dram__bytes_write.sum of the captured launch (ncu --set full, profiles/ncu_prefill_r1.txt)
-NCU_TRAFFIC_BYTES = 223.15e6 + 110.06e6
-NCU_TRAFFIC_NOTE = ("ncu capture of the 28672x8192 M=2048 launch: 223.2 MB read + 110.1 MB written; algorithmic bytes of that "
-                    "launch 314 MB (packed W 176 + X 17 + D 117 + scales 4)")
-WORKLOAD = "llama2-70b linears {8192x8192, 28672x8192, 8192x28672} W6A6 g128 prefill M=2048"
+# (name, N, K, tensor-parallel mode)
+LAYERS = [("attn_o_8192x8192", 8192, 8192, "row"),
+          ("mlp_gate_28672x8192", 28672, 8192, "column"),
+          ("mlp_down_8192x28672", 8192, 28672, "row")]
+# dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (28672x8192, M=2048): a CONSTANT taken from the ncu
+# capture committed as profiles/ncu_prefill_r2.txt (ncu is not run inside the bench), stated as such in the JSON line
+NCU_TRAFFIC_BYTES = 238.48e6 + 115.53e6
+NCU_TRAFFIC_NOTE = ("constant from profiles/ncu_prefill_r2.txt (ncu --set full of the 28672x8192 M=2048 launch: 238.5 MB read + "
+                    "115.5 MB written), not measured in this run; algorithmic bytes of that launch 314 MB (packed W 176 + X 17 + D 117 + scales 4)")
+
+
+def workload(xb):
+    return (f"llama2-70b linears {{8192x8192, 28672x8192, 8192x28672}} W6A{xb} g128 prefill M=2048 "
+            "(A6 and A8 activations both travel in int8 containers: same bytes, same MMAs)")
 
 
 def peaks():
@@ -112,16 +117,16 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU fake-quant path on the host cores
 # --------------------------------------------------------------------------------------------
-def cpu_reference_run(steps: int, warmup: int, sample_rows: int):
+def cpu_reference_run(steps: int, warmup: int, sample_rows: int, ab: int = 6):
     from oracle.fakequant_torch import FakeQuantLinearCPU      # baseline leg: the only oracle use here
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
     mods, xs = [], []
-    for _, N, K, _, ab in LAYERS:
+    for _, N, K, _ in LAYERS:
         mods.append(FakeQuantLinearCPU(0.02 * torch.randn(N, K, generator=g), ab, faithful=True))
         xs.append(torch.randn(sample_rows, K, generator=g))
-    ops = sum(2.0 * sample_rows * N * K for _, N, K, _, _ in LAYERS)
+    ops = sum(2.0 * sample_rows * N * K for _, N, K, _ in LAYERS)
     for _ in range(warmup):
         for m, x in zip(mods, xs):
             m(x)
@@ -140,11 +145,11 @@ def run_reference_arm(args):
     if rank != 0:
         return
     steps, warmup = min(args.steps, 3), min(args.warmup, 1)
-    tops, ms, cores, sample = cpu_reference_run(steps, warmup, sample_rows=32)
-    line = {"impl": "reference", "metric": "W6A6 GEMM TOPS (2*M*N*K/t), llama2-70b linear layers", "value": tops,
+    tops, ms, cores, sample = cpu_reference_run(steps, warmup, sample_rows=32, ab=args.xbits)
+    line = {"impl": "reference", "metric": f"W6A{args.xbits} GEMM TOPS (2*M*N*K/t), llama2-70b linear layers", "value": tops,
             "unit": "TOPS", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "arm": "reference CPU fake-quant path (oracle port)"},
+            "config": {"workload": workload(args.xbits), "arm": "reference CPU fake-quant path (oracle port)"},
             "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -155,9 +160,10 @@ def run_reference_arm(args):
 # --config c1: BASELINE.json configs[0], the reference's own CPU-runnable case, as a side record
 # --------------------------------------------------------------------------------------------
 def run_c1():
-    """nn.Linear(4096, 4096, bias=False) default init under torch.manual_seed(0), x = randn(16, 4096), W6A6 g128:
+    """nn.Linear(4096, 4096, bias=False) default init under torch.manual_seed(0), x = randn(16, 4096), W6A6 g128, fp32:
     the reference's CPU fake-quant forward (faithful = weights re-quantised per call, and pre-quantised) on all host
-    cores beside the fused CUDA path; outputs compared."""
+    cores beside the CUDA path on the same fp32 module (fp32-arithmetic quantisers, flexq_quant_act_f32 /
+    flexq_quant_pack_w6_f32); outputs compared."""
     from oracle.fakequant_torch import FakeQuantLinearCPU      # baseline leg
     from flexq_b200 import QuantLinear, model_pack
     torch.manual_seed(0)
@@ -175,35 +181,106 @@ def run_c1():
 
     ms_f, y_cpu = cpu_ms(FakeQuantLinearCPU(lin.weight.detach(), 6, faithful=True), 5)
     ms_p, _ = cpu_ms(FakeQuantLinearCPU(lin.weight.detach(), 6, faithful=False), 20)
-    q = QuantLinear(lin.half().cuda(), model_pack.default_quant_params(6, True), model_pack.default_quant_params(6, False))
+    q = QuantLinear(lin.cuda(), model_pack.default_quant_params(6, True), model_pack.default_quant_params(6, False))
     q.set_quant_state(True, True)
-    xg = x.half().cuda()
+    xg = x.cuda()
     y = q(xg)
+    us = graph_time_us([lambda: q(xg)], iters_per_copy=20)
+    ref = y_cpu.double()
+    err = (y.double().cpu() - ref)
+    line = {"config": "C1: QuantLinear W6A6 g128, nn.Linear(4096,4096) seed 0, x = randn(16,4096), fp32 module",
+            "cpu_faithful_ms": ms_f, "cpu_prequantized_ms": ms_p, "cpu_cores": cores, "cpu_kind": "port (oracle/fakequant_torch.py, fp32)",
+            "gpu_us_graph": us, "speedup_vs_faithful": ms_f * 1e3 / us, "speedup_vs_prequantized": ms_p * 1e3 / us,
+            "rms_rel_vs_cpu_fp32": float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()),
+            "max_abs_over_mean_abs": float(err.abs().max() / ref.abs().mean()),
+            "tolerance": "rms-rel <= 1e-3, max-abs <= 1e-2 * mean|ref| (tests/test_gpu_parity.py)",
+            "note": "same integers and fp32 activation scales as the CPU path; weight scales rounded to fp16, fp16 GEMM output"}
+    print(json.dumps(line), flush=True)
+
+
+def graph_time_us(fn_list, iters_per_copy=4, reps=5):
+    """Mean us per call from CUDA-graph replays of the calls in fn_list (one per rotated weight copy)."""
+    torch.cuda.synchronize()
+    for f in fn_list:
+        f()
+    torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        q(xg)
-    torch.cuda.current_stream().wait_stream(s)
-    with torch.cuda.graph(g):
-        q(xg)
-    for _ in range(5):
-        g.replay()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(200):
-        g.replay()
-    e1.record()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(iters_per_copy):
+                for f in fn_list:
+                    f()
+    n = iters_per_copy * len(fn_list)
+    g.replay()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / 200 * 1e3
-    ref = y_cpu.double()
-    err = (y.double().cpu() - ref)
-    line = {"config": "C1: QuantLinear W6A6 g128, nn.Linear(4096,4096) seed 0, x = randn(16,4096)",
-            "cpu_faithful_ms": ms_f, "cpu_prequantized_ms": ms_p, "cpu_cores": cores, "cpu_kind": "port (oracle/fakequant_torch.py, fp32)",
-            "gpu_fused_us_graph": us, "speedup_vs_faithful": ms_f * 1e3 / us, "speedup_vs_prequantized": ms_p * 1e3 / us,
-            "rms_rel_vs_cpu_fp32": float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()),
-            "note": "GPU path quantises in fp16 (module dtype) and rounds activations half-away; CPU port is the fp32 fake-quant forward"}
-    print(json.dumps(line), flush=True)
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3 / n)
+    return best
+
+
+# --------------------------------------------------------------------------------------------
+# side records the metric asks for ("... vs M ...; decode tok/s"), measured in the same run at N = 1 and attached
+# to the JSON line under "extra" (the headline stays the M = 2048 step)
+# --------------------------------------------------------------------------------------------
+def extra_records(capi, layers, fp16_w, dev, xb, hbm_gbs):
+    extra = {}
+    L2 = 126 << 20
+    # decode: fused quantise + GEMM at M = 1 and 16 under a CUDA graph, weights rotated through > 2 x L2 of copies
+    dec = []
+    for (name, N, K, _), lin in zip(LAYERS, layers):
+        wbytes = lin.w6.numel()
+        ncopy = max(1, min(8, (2 * L2 + wbytes - 1) // wbytes))
+        copies = [(lin.w6, lin.w_scale)] + [(lin.w6.clone(), lin.w_scale.clone()) for _ in range(ncopy - 1)]
+        for M in (1, 16):
+            x = torch.randn(M, K, device=dev).half()
+            out = torch.empty(M, N, dtype=torch.float16, device=dev)
+            ws = capi.new_workspace(M, K)
+            us = graph_time_us([lambda c=c: capi.linear_w6ax(x, c[0], c[1], N, xb, ws, capi.ROUND_CUDA, out) for c in copies])
+            nbytes = N * K * 6 // 8 + N * (K // 128) * 2 + M * K * 2 + M * N * 2
+            dec.append({"shape": f"{N}x{K}", "M": M, "us": us, "hbm_gbs": nbytes / us / 1e3, "hbm_frac": nbytes / us / 1e3 / hbm_gbs})
+        del copies
+    extra["decode"] = dec
+    extra["decode_note"] = ("fused activation quantise + W6Ax GEMM, CUDA-graph replays, weight copies rotated (> 2 x L2); bytes = packed W + "
+                            "w-scales + fp16 X + fp16 D; hbm_frac against hbm_gbs of MEASURED_PEAKS.json")
+    # M = 2048 GEMM beside cuBLAS FP16 (torch.matmul) and cuBLAS INT8 (torch._int_mm) on the same shapes
+    vs = []
+    for (name, N, K, _), lin, w in zip(LAYERS, layers, fp16_w):
+        M = M_TOKENS
+        x = torch.randn(M, K, device=dev).half()
+        xq, sx = capi.quant_act(x, xb)
+        out = torch.empty(M, N, dtype=torch.float16, device=dev)
+        gws = capi.new_workspace()
+        rec = {"shape": f"{N}x{K}", "M": M,
+               "w6ax_gemm_us": graph_time_us([lambda: capi.gemm_w6ax(xq, sx, lin.w6, lin.w_scale, N, gws, out)]),
+               "cublas_f16_us": graph_time_us([lambda: torch.matmul(x, w.t(), out=out)])}
+        try:
+            xi8 = torch.randint(-32, 32, (M, K), device=dev, dtype=torch.int8)
+            wi8 = torch.randint(-32, 32, (K, N), device=dev, dtype=torch.int8)
+            rec["cublas_i8_us"] = graph_time_us([lambda: torch._int_mm(xi8, wi8)])
+            del xi8, wi8
+        except Exception as e:                       # noqa: BLE001
+            rec["cublas_i8_err"] = str(e)[:80]
+        rec["vs_cublas_f16"] = rec["cublas_f16_us"] / rec["w6ax_gemm_us"]
+        vs.append(rec)
+    extra["vs_cublas"] = vs
+    return extra
+
+
+def decode_tok_s_record():
+    """80-layer LLaMA-2-70B W6 chain (norms, residuals, SiLU*up through the fused producers, all linears; no attention /
+    KV) under one CUDA graph: tools/decode_stack.py --chain --fuse-gate-up."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import decode_stack
+    recs = decode_stack.run_stack("llama2-70b", 80, [1, 16], True, True, with_fp16=False, clone_layers=True, verbose=False)
+    return [{"batch": r["batch"], "layers": r["layers"], "us_per_step": r["w6ax_us"], "tok_s": r["w6ax_tok_s"], "hbm_frac": r["hbm_frac"]} for r in recs]
 
 
 # --------------------------------------------------------------------------------------------
@@ -216,6 +293,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="flexq_b200", choices=["flexq_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side records (decode, cuBLAS comparators, 80-layer decode chain)")
+    ap.add_argument("--xbits", type=int, default=6, choices=[6, 8],
+                    help="activation bits: 6 = BASELINE.json configs[2] (default), 8 = configs[4] (the W6A8 tensor-parallel stack)")
     ap.add_argument("--config", default="c3", choices=["c3", "c1"], help="c3 = the bench workload (default); c1 = side record")
     args = ap.parse_args()
     if args.config == "c1":
@@ -225,6 +305,7 @@ def main():
         run_reference_arm(args)
         return
     args.warmup = max(args.warmup, 3)
+    xb = args.xbits
 
     import torch.distributed as dist
     from flexq_b200 import capi, tp
@@ -240,28 +321,32 @@ def main():
     capi.load()
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs a moment before its first sample
 
-    # ---- build the (sharded) layers: synthetic random-init weights, packed offline on the GPU
+    # ---- build the (sharded) layers: synthetic random-init weights (the same full matrices on every rank, each rank
+    # packs its shard offline on the GPU); rank 0 keeps what the tp check below needs
     torch.manual_seed(1234)
-    layers, x_dev, x_host, y_host = [], [], [], []
-    for name, N, K, mode, ab in LAYERS:
-        Nl, Kl = (N // world, K) if mode == "column" else (N, K // world)
-        w = (0.02 * torch.randn(Nl, Kl, device=dev)).half()
+    layers, x_dev, x_host, y_host, fp16_w, check = [], [], [], [], [], []
+    for name, N, K, mode in LAYERS:
+        w_full = (0.02 * torch.randn(N, K, device=dev)).half()
+        x_full = torch.randn(M_TOKENS, K, device=dev).half()
+        w = w_full if world == 1 else tp.shard_weight(w_full, mode, rank, world)
+        x = x_full if (world == 1 or mode == "column") else tp.shard_activation(x_full, rank, world)
+        Nl, Kl = w.shape
         w6, wsc = capi.quant_pack_w6(w)
-        del w
-        lin = tp.TPLinearW6Ax.from_packed(w6, wsc, Nl, Kl, mode, ab, rank, world)
+        if world > 1 and rank == 0:                  # a 256 x 256 output block recomputed at tp = 1 after the timed region
+            check.append((x_full[:256].clone(), w_full[:256].clone()))
+        fp16_w.append(w if world == 1 and not args.no_extra else None)
+        del w_full, x_full
+        lin = tp.TPLinearW6Ax.from_packed(w6, wsc, Nl, Kl, mode, xb, rank, world)
         layers.append(lin)
-        x = torch.randn(M_TOKENS, Kl, device=dev).half()
         x_dev.append(x)
         x_host.append(x.cpu().pin_memory())
-        y_host.append(torch.empty(M_TOKENS, Nl, dtype=torch.float16).pin_memory())
     outs = [torch.empty(M_TOKENS, l.N, dtype=torch.float16, device=dev) for l in layers]
-    total_ops = sum(2.0 * M_TOKENS * N * K for _, N, K, _, _ in LAYERS)
+    total_ops = sum(2.0 * M_TOKENS * N * K for _, N, K, _ in LAYERS)
     stream = torch.cuda.current_stream()
 
     # Row-parallel reduction: our peer-memory all-reduce (flexq_allreduce_sum_synced_f16 over NVLink / NVSwitch symmetric
     # memory).  tp = 8: NVSwitch multicast path, two token chunks so the reduction of chunk 0 overlaps the GEMM of chunk 1
-    # on 8 SMs the GEMM leaves free (measured: 196 us vs 288 us with NCCL for down_proj).  tp = 2, 4: peer-pointer path
-    # after the whole GEMM (the 32 MB reduction alone: 69 / 96 us vs NCCL 83 / 119 us).
+    # on 8 SMs the GEMM leaves free.  tp = 2, 4: peer-pointer path after the whole GEMM.
     # FLEXQ_BENCH_AR=nccl|peer overrides.  Any failure to set up symmetric memory falls back to NCCL.
     ar_mode = "nccl"
     want_peer = os.environ.get("FLEXQ_BENCH_AR", "peer") == "peer"
@@ -285,18 +370,25 @@ def main():
                 lin._ar = None
 
     def step_device():
+        res = []
         for lin, x, o in zip(layers, x_dev, outs):
             if getattr(lin, "_ar", None) is not None:
-                lin.forward(x)                                # result stays in the symmetric buffer
+                res.append(lin.forward(x))                    # result stays in the symmetric buffer
             else:
-                lin.forward(x, o)
+                res.append(lin.forward(x, o))
+        return res
 
     # end to end: pinned host activations in, pinned host outputs back, through the host-buffer front end
-    # (H2D / kernels / D2H on three streams, per-layer staging buffers -- flexq_b200/host_io.py)
+    # (H2D / kernels / D2H on three streams, per-layer staging buffers -- flexq_b200/host_io.py).  Every rank holds the
+    # all-reduced output of a row-parallel layer: rank r hands rows [r*M/tp, (r+1)*M/tp) to the host, so the D2H traffic
+    # of the job is one copy of every output, spread over the ranks' PCIe links; sharded outputs go back from every rank.
     from flexq_b200.host_io import HostStagedLinears
-    # replicated (all-reduced) outputs go back to the host from rank 0 only; sharded outputs from every rank
-    copy_out = [not (mode == "row" and world > 1 and rank != 0) for _, _, _, mode, _ in LAYERS]
-    pipe = HostStagedLinears(layers, M_TOKENS, dev, copy_out)
+    rows = []
+    for (_, N, K, mode), lin in zip(LAYERS, layers):
+        r0, r1 = (rank * M_TOKENS // world, (rank + 1) * M_TOKENS // world) if (mode == "row" and world > 1) else (0, M_TOKENS)
+        rows.append((r0, r1))
+        y_host.append(torch.empty(r1 - r0, lin.N, dtype=torch.float16).pin_memory())
+    pipe = HostStagedLinears(layers, M_TOKENS, dev, rows)
 
     def timed_e2e(steps, warmup):
         for _ in range(warmup):
@@ -345,30 +437,46 @@ def main():
     ms_step = timed(step_device, args.steps, args.warmup)
     ms_e2e = timed_e2e(max(5, args.steps // 2), 3)
 
-    # ---- dominant kernel (the W6A6 GEMM) timed alone on pre-quantised operands -> roofline
+    # ---- dominant kernel (the W6Ax GEMM) timed alone on pre-quantised operands -> roofline
     pre = []
-    if True:
-        for lin, x in zip(layers, x_dev):
-            xq, sx = capi.quant_act(x, lin.x_bits, capi.ROUND_CUDA)
-            pre.append((xq, sx))
-        gws = capi.new_workspace()
+    for lin, x in zip(layers, x_dev):
+        xq, sx = capi.quant_act(x, lin.x_bits, capi.ROUND_CUDA)
+        pre.append((xq, sx))
+    gws = capi.new_workspace()
 
-        def gemm_only():
-            for lin, (xq, sx), o in zip(layers, pre, outs):
-                capi.gemm_w6ax(xq, sx, lin.w6, lin.w_scale, lin.N, gws, o)
+    def gemm_only():
+        for lin, (xq, sx), o in zip(layers, pre, outs):
+            capi.gemm_w6ax(xq, sx, lin.w6, lin.w_scale, lin.N, gws, o)
 
-        ms_gemm = timed(gemm_only, args.steps, 3)
-        if sampler:
-            sampler.end()
-        clocks = sampler.stop(extend=step_device if world == 1 else None) if sampler else None
-        _, bf16_tf, src = peaks()
-        peak = 2.0 * bf16_tf                       # kind::i8 issues at twice the bf16 rate on sm_100
-        achieved = total_ops / world / (ms_gemm * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOPS", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES if world == 1 else None, "traffic_note": NCU_TRAFFIC_NOTE,
-                "kernel": "w6ax_gemm_kernel<M_TILE=192,GP=1>", "launches_per_step": len(LAYERS),
-                "avg_launch_ms": ms_gemm / len(LAYERS),
-                "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({src}); int8 dense = 2x bf16 dense on sm_100"}
+    ms_gemm = timed(gemm_only, args.steps, 3)
+    if sampler:
+        sampler.end()
+    clocks = sampler.stop(extend=step_device if world == 1 else None) if sampler else None
+    hbm_gbs, bf16_tf, src = peaks()
+    peak = 2.0 * bf16_tf                       # kind::i8 issues at twice the bf16 rate on sm_100
+    achieved = total_ops / world / (ms_gemm * 1e-3) / 1e12
+    roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOPS", "frac": achieved / peak,
+            "traffic": NCU_TRAFFIC_BYTES if world == 1 else None, "traffic_note": NCU_TRAFFIC_NOTE,
+            "kernel": "flexq::w6ax_gemm_kernel (the 192-token-tile instantiation at this M)", "launches_per_step": len(LAYERS),
+            "avg_launch_ms": ms_gemm / len(LAYERS),
+            "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({src}); int8 dense = 2x bf16 dense on sm_100"}
+
+    # ---- tensor-parallel numerics: a 256 x 256 block of every layer's output on rank 0 against the same block computed
+    # at tp = 1 from the unsharded weight rows and activations (fp16 partial sums are rounded before the reduction, so
+    # row-parallel outputs agree to fp16 rounding, column-parallel ones exactly)
+    tp_check = None
+    if world > 1:
+        res = step_device()
+        torch.cuda.synchronize()
+        if rank == 0:
+            tp_check = []
+            for (name, N, K, mode), y, (xb256, wb256) in zip(LAYERS, res, check):
+                w6b, wscb = capi.quant_pack_w6(wb256)
+                ref = capi.linear_w6ax(xb256, w6b, wscb, 256, xb, capi.new_workspace(256, K)).float()
+                got = y[:256, :256].float()
+                err = (got - ref).abs()
+                tp_check.append({"layer": name, "mode": mode, "max_abs_over_mean_abs": float(err.max() / ref.abs().mean()),
+                                 "rms_rel": float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())})
 
     if rank != 0:
         if world > 1:
@@ -377,27 +485,39 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        tops, _, cores, sample = cpu_reference_run(steps=2, warmup=1, sample_rows=32)
+        tops, _, cores, sample = cpu_reference_run(steps=2, warmup=1, sample_rows=32, ab=xb)
         cpu = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample}
 
+    extra = None
+    if world == 1 and not args.no_extra:
+        extra = extra_records(capi, layers, fp16_w, dev, xb, hbm_gbs)
+        del layers, fp16_w, x_dev, outs, pre, pipe
+        torch.cuda.empty_cache()
+        try:
+            extra["decode_tok_s"] = decode_tok_s_record()
+            extra["decode_tok_s_note"] = ("LLaMA-2-70B, all 80 layers, W6A6 (down_proj W6A8), synthetic weights, one CUDA graph per token step: "
+                                          "norms, residuals, SiLU*up and every linear; attention / KV cache excluded")
+        except Exception as e:                       # noqa: BLE001
+            extra["decode_tok_s_err"] = str(e)[:200]
+
     h2d = sum(x.numel() * 2 for x in x_host)
-    d2h = sum(y.numel() * 2 for y, c in zip(y_host, copy_out) if c)
+    d2h = sum(y.numel() * 2 for y in y_host)
     line = {
-        "metric": "W6A6 GEMM TOPS (2*M*N*K/t), llama2-70b linear layers", "value": total_ops / (ms_step * 1e-3) / 1e12,
+        "metric": f"W6A{xb} GEMM TOPS (2*M*N*K/t), llama2-70b linear layers", "value": total_ops / (ms_step * 1e-3) / 1e12,
         "unit": "TOPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tokens": M_TOKENS, "parallelism": f"tp{world}",
+        "config": {"workload": workload(xb), "tokens": M_TOKENS, "x_bits": xb, "parallelism": f"tp{world}",
                    "l2": "per-step working set (384 MB packed weights + activations) exceeds the 126 MB L2",
-                   "step": "fused activation quantise + W6A6 GEMM per layer" + (
+                   "step": "fused activation quantise + W6Ax GEMM per layer" + (
                        "" if world == 1 else " + NCCL all-reduce on row-parallel layers" if ar_mode == "nccl" else
                        " + peer-memory all-reduce (own kernel, NVLink symmetric memory) on row-parallel layers"
                        + (f", {ar_chunks} token chunks overlapped with the GEMM" if ar_chunks > 1 else ""))},
         "e2e": {"value": total_ops / (ms_e2e * 1e-3) / 1e12, "unit": "TOPS", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "bytes_are": "per rank (every rank copies its own shard / row slice)",
                 "path": "pinned host x -> H2D -> fused quantise + GEMM -> D2H -> pinned host y, every layer every step; "
                         "three streams so copies in both directions overlap the kernels"},
         "gpu_launches": 2 * len(LAYERS) * args.steps,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "tp_check": tp_check, "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -98,6 +98,29 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_device(fn):
+    """Run a wrapper with the CUDA device of its tensor arguments current (so that the launch, the stream taken by
+    _stream() and the outputs allocated inside all belong to that device) and check that the operands share it.
+    A model spread over several GPUs in one process (device_map='auto', as the reference's evaluation flow loads
+    large models) calls into the library from whatever device happens to be current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise FlexQError(f"{fn.__name__}: operands on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
 def ceil4(m: int) -> int:
     return (m + 3) // 4 * 4
 
@@ -111,6 +134,7 @@ def new_workspace(M: int | None = None, K: int | None = None, device="cuda") -> 
     return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
+@_on_device
 def bit_packing_i32(ints: torch.Tensor, bits: int) -> torch.Tensor:
     R, K = ints.shape
     out = torch.empty(R * K * bits // 32, dtype=torch.int32, device=ints.device)
@@ -118,6 +142,7 @@ def bit_packing_i32(ints: torch.Tensor, bits: int) -> torch.Tensor:
     return out
 
 
+@_on_device
 def bit_packing_f16(x: torch.Tensor, bits: int):
     M, K = x.shape
     planes = torch.empty(M * K * bits // 32, dtype=torch.int32, device=x.device)
@@ -126,6 +151,7 @@ def bit_packing_f16(x: torch.Tensor, bits: int):
     return planes, xs
 
 
+@_on_device
 def quant_act(x: torch.Tensor, bits: int, mode: int = ROUND_CUDA):
     """fp16 activations -> int8 containers + fp32 scales (mode selects the reference behaviour); fp32 activations
     always take the python quantiser's fp32 arithmetic (flexq_quant_act_f32)."""
@@ -140,6 +166,7 @@ def quant_act(x: torch.Tensor, bits: int, mode: int = ROUND_CUDA):
     return xq, sx
 
 
+@_on_device
 def rmsnorm_quant(x: torch.Tensor, gamma: torch.Tensor, eps: float, bits: int, residual: torch.Tensor | None = None,
                   want_normed: bool = False):
     """Fused (residual add +) RMSNorm + activation quantise.  `residual` is updated in place to x + residual.
@@ -154,6 +181,7 @@ def rmsnorm_quant(x: torch.Tensor, gamma: torch.Tensor, eps: float, bits: int, r
     return xq, sx, normed
 
 
+@_on_device
 def silu_mul_quant(gate: torch.Tensor, up: torch.Tensor, bits: int = 8, want_out: bool = False):
     """Fused SiLU(gate) * up + activation quantise.  gate/up: [M, K] fp16 views with equal row stride
     (e.g. the two halves of a fused gate_up output).  Returns (xq, sx, out or None)."""
@@ -174,6 +202,7 @@ def _new_w6(N, K, device):
     return torch.empty(load().flexq_w6_packed_bytes(N, K), dtype=torch.uint8, device=device)
 
 
+@_on_device
 def pack_w6(w_int: torch.Tensor) -> torch.Tensor:
     N, K = w_int.shape
     w6 = _new_w6(N, K, w_int.device)
@@ -182,6 +211,7 @@ def pack_w6(w_int: torch.Tensor) -> torch.Tensor:
     return w6
 
 
+@_on_device
 def quant_pack_w6(w: torch.Tensor):
     N, K = w.shape
     w6 = _new_w6(N, K, w.device)
@@ -191,12 +221,14 @@ def quant_pack_w6(w: torch.Tensor):
     return w6, ws
 
 
+@_on_device
 def planes_to_i8(planes: torch.Tensor, R: int, K: int, bits: int) -> torch.Tensor:
     out = torch.empty(R, K, dtype=torch.int8, device=planes.device)
     check(load().flexq_planes_to_i8(_ptr(planes), _ptr(out), R, K, bits, _stream()), "flexq_planes_to_i8")
     return out
 
 
+@_on_device
 def planes_to_w6(planes: torch.Tensor, N: int, K: int) -> torch.Tensor:
     w6 = _new_w6(N, K, planes.device)
     scratch = torch.empty(N, K, dtype=torch.int8, device=planes.device)
@@ -204,18 +236,21 @@ def planes_to_w6(planes: torch.Tensor, N: int, K: int) -> torch.Tensor:
     return w6
 
 
+@_on_device
 def xscale_ref_to_sx(xs: torch.Tensor, M: int, K: int) -> torch.Tensor:
     sx = torch.empty(K // GROUP, ceil4(M), dtype=torch.float32, device=xs.device)
     check(load().flexq_xscale_ref_to_sx(_ptr(xs), _ptr(sx), M, K, _stream()), "flexq_xscale_ref_to_sx")
     return sx
 
 
+@_on_device
 def w6_to_i8(w6: torch.Tensor, N: int, K: int) -> torch.Tensor:
     out = torch.empty(N, K, dtype=torch.int8, device=w6.device)
     check(load().flexq_w6_to_i8(_ptr(w6), _ptr(out), N, K, _stream()), "flexq_w6_to_i8")
     return out
 
 
+@_on_device
 def gemm_w6ax(xq, sx, w6, w_scale, N: int, workspace: torch.Tensor, out: torch.Tensor | None = None):
     M, K = xq.shape
     if out is None:
@@ -225,6 +260,7 @@ def gemm_w6ax(xq, sx, w6, w_scale, N: int, workspace: torch.Tensor, out: torch.T
     return out
 
 
+@_on_device
 def gemm_w6ax_groupsums(xq, w6, N: int) -> torch.Tensor:
     M, K = xq.shape
     S = torch.empty(M, N, K // GROUP, dtype=torch.int32, device=xq.device)
@@ -232,6 +268,7 @@ def gemm_w6ax_groupsums(xq, w6, N: int) -> torch.Tensor:
     return S
 
 
+@_on_device
 def linear_w6ax(x, w6, w_scale, N: int, x_bits: int, workspace: torch.Tensor, mode: int = ROUND_CUDA,
                 out: torch.Tensor | None = None):
     M, K = x.shape
@@ -242,6 +279,7 @@ def linear_w6ax(x, w6, w_scale, N: int, x_bits: int, workspace: torch.Tensor, mo
     return out
 
 
+@_on_device
 def gemm_ref_layout(x_planes, x_scale, w6, w_scale, M: int, N: int, K: int, x_bits: int, workspace: torch.Tensor):
     out = torch.empty(M, N, dtype=torch.float16, device=w6.device)
     check(load().flexq_gemm_ref_layout(_ptr(x_planes), _ptr(x_scale), _ptr(w6), _ptr(w_scale), _ptr(out), M, N, K, x_bits,
@@ -265,6 +303,7 @@ def allreduce_sum_synced_f16(multicast_ptr: int, peer_ptrs, flag_ptrs, offset_el
                                                 _stream()), "flexq_allreduce_sum_synced_f16")
 
 
+@_on_device
 def allreduce_oneshot_f16(data_ptrs, flag_ptrs, elems: int, rank: int, world: int, out: torch.Tensor):
     """One-kernel decode all-reduce over symmetric memory (see the header)."""
     d = (ctypes.c_void_p * 8)(*([int(p) for p in data_ptrs] + [0] * (8 - len(data_ptrs))))

@@ -15,8 +15,9 @@ import torch
 
 class HostStagedLinears:
     def __init__(self, layers, max_tokens: int, device: torch.device, copy_out=None):
-        """`copy_out[i]` False skips the D2H of layer i on this rank (tensor parallel: the all-reduced output of
-        a row-parallel layer is identical on every rank, only one of them needs to hand it to the host)."""
+        """`copy_out[i]`: what this rank hands back to the host for layer i -- True (all rows), False (nothing) or a row
+        range (r0, r1).  Tensor parallel: the all-reduced output of a row-parallel layer is identical on every rank, so
+        each rank returns its own slice of the rows and the job's D2H traffic is spread over all PCIe links."""
         self.layers = list(layers)
         self.copy_out = list(copy_out) if copy_out is not None else [True] * len(self.layers)
         self.dev = device
@@ -49,7 +50,10 @@ class HostStagedLinears:
                 self.ev_comp[i].record(self.s_comp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_comp[i])
-                if self.copy_out[i]:
+                co = self.copy_out[i]
+                if isinstance(co, tuple):
+                    yh.copy_(yd[co[0]:co[1]], non_blocking=True)
+                elif co:
                     yh.copy_(yd, non_blocking=True)
                 self.ev_out[i].record(self.s_out)
         self.passes += 1

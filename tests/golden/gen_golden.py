@@ -92,6 +92,20 @@ def main():
         for k, v in linear_case(*args).items():
             out[f"{name}/{k}"] = v
     np.savez_compressed(os.path.join(HERE, "linear_golden.npz"), **out)
+
+    # BASELINE.json configs[0]: nn.Linear(4096, 4096, bias=False) default init under
+    # torch.manual_seed(0), x = randn(16, 4096), fp32 on the CPU through the reference's QuantLinear.  Only the output
+    # is stored (fp16-rounded to keep the fixture small would lose the point: fp32, 256 KB); the test regenerates w and x
+    # from the same seed and checks their checksums.
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4096, 4096, bias=False)
+    x = torch.randn(16, 4096)
+    ql = QuantLinear(lin, params(6, [0]), params(6, []))
+    ql.set_quant_state(True, True)
+    with torch.no_grad():
+        y = ql(x)
+    np.savez_compressed(os.path.join(HERE, "c1_golden.npz"), y=y.numpy(), w_sum=np.float64(lin.weight.double().sum().item()),
+                        w_abs_sum=np.float64(lin.weight.double().abs().sum().item()), x_sum=np.float64(x.double().sum().item()))
     print("wrote", [f for f in os.listdir(HERE) if f.endswith(".npz")])
 
 

@@ -149,6 +149,25 @@ def test_quant_act_python_mode(capi, oracle, M, K, bits):
     assert np.array_equal(sx.cpu().numpy()[:, :M].T, s_ref.astype(np.float32))
 
 
+@pytest.mark.parametrize("M,K,bits", [(1, 128, 6), (5, 384, 6), (16, 4096, 6), (16, 4096, 8), (33, 1024, 8), (300, 256, 6)])
+def test_quant_act_f32_matches_python_quantiser(capi, oracle, M, K, bits):
+    """fp32 activations (the reference's CPU-runnable configuration): integers and fp32 scales bit exact against the
+    oracle's fp32 evaluation of UniformAffineQuantizer, which tests/golden pins to the reference (q_a*_f32_* cases);
+    includes an all-zero group (scale clamps to 1e-5), a tiny group and exact .5 ties (round half to even)."""
+    rng = np.random.default_rng(M * 5 + bits)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    x[0, :128] = 0.0
+    if M > 1:
+        x[1, :128] = 1e-7
+    if M > 2:
+        x[2, :128] = (np.arange(128) - 63.5).astype(np.float32)
+    q_ref, s_ref, _ = oracle.quant_sym_python(x, bits)
+    xq, sx = capi.quant_act(torch.from_numpy(x).cuda(), bits)
+    assert np.array_equal(xq.cpu().numpy().astype(np.int32), q_ref)
+    assert np.array_equal(sx.cpu().numpy()[:, :M].T.view(np.uint32), s_ref.astype(np.float32).view(np.uint32))
+    assert not sx.cpu().numpy()[:, M:].any()
+
+
 @pytest.mark.parametrize("M,K,bits", [(1, 128, 6), (4, 384, 8), (8, 1024, 6), (16, 512, 6)])
 def test_bit_packing_f16_reference_layout(capi, oracle, M, K, bits):
     x = _act_inputs(np.random.default_rng(M), M, K)
@@ -364,6 +383,49 @@ def test_quantlinear_module_vs_reference_golden(capi, case):
     assert y3.shape == (1, x.shape[0], w.shape[0]) and torch.equal(y3[0], y)
 
 
+@pytest.mark.parametrize("case", ["lin_w6a6_f32", "lin_w6a8_f32", "c1"])
+def test_quantlinear_fp32_module_vs_reference_golden(capi, case):
+    """fp32 modules: flexq_b200.QuantLinear against the outputs of the reference's own QuantLinear run in fp32 on the
+    CPU (tests/golden, generated by importing /root/reference/algorithm).  `c1` is BASELINE.json configs[0]:
+    nn.Linear(4096, 4096, bias=False) default init under torch.manual_seed(0), x = randn(16, 4096), W6A6 g128.
+    Tolerance as stated for fp16 outputs (rms-rel <= 1e-3, max-abs <= 1e-2 * mean|ref|): integers and activation scales
+    are the reference's, the weight scales are its fp32 scales rounded to fp16 (2^-12 relative) and the GEMM stores fp16."""
+    import os
+    import torch.nn as nn
+    from flexq_b200 import QuantLinear
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    if case == "c1":
+        g = np.load(os.path.join(gdir, "c1_golden.npz"))
+        torch.manual_seed(0)
+        lin = nn.Linear(4096, 4096, bias=False)
+        x = torch.randn(16, 4096)
+        assert abs(lin.weight.double().sum().item() - float(g["w_sum"])) < 1e-9 and abs(x.double().sum().item() - float(g["x_sum"])) < 1e-9, \
+            "torch's seeded CPU initialisation differs from the build container's: fixture not applicable"
+        y_ref, ab = g["y"], 6
+    else:
+        g = np.load(os.path.join(gdir, "linear_golden.npz"))
+        w, xn, y_ref, ab = g[case + "/w"], g[case + "/x"], g[case + "/y"], int(g[case + "/abits"])
+        lin = nn.Linear(w.shape[1], w.shape[0], bias=False)
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(w))
+        x = torch.from_numpy(xn)
+    lin = lin.cuda()
+    p = dict(n_bits=6, per_channel_axes=[0], symmetric=True, dynamic_method="per_group", group_size=128, disable_zero_point=True)
+    ql = QuantLinear(lin, p, dict(p, n_bits=ab, per_channel_axes=[]))
+    ql.set_quant_state(True, True)
+    assert ql.kernel_supported()
+    y = ql(x.cuda())
+    assert y.dtype == torch.float32 and tuple(y.shape) == y_ref.shape
+    _check_close(y.cpu().numpy(), y_ref)
+    if case != "c1":
+        # weights: the reference's integers, and its fp32 scales to fp16 precision
+        w6, wsc = ql.pack_weights()
+        wq = capi.w6_to_i8(w6, w.shape[0], w.shape[1]).cpu().numpy().astype(np.float32).reshape(w.shape[0], -1, 128)
+        sc = g[case + "/wscale"]
+        assert np.array_equal(wq, np.rint(g[case + "/wdeq"].reshape(w.shape[0], -1, 128) / sc[:, :, None]))
+        assert np.array_equal(wsc.cpu().numpy().T, sc.astype(np.float16))
+
+
 def test_host_staged_pipeline_matches_direct_call(capi):
     """Host-buffer front end (three-stream pipeline) returns what the direct device call does,
     pass after pass (staging buffers are reused)."""
@@ -522,9 +584,9 @@ def test_gemm_every_decomposition_vs_exact(capi, M, N, K, xb):
         err = (o.double() - ref).abs()
         assert (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() <= RMS_REL_TOL
         assert (err.max() / ref.abs().mean()).item() <= MAXABS_REL_TOL
-    if M >= 2048:
-        # several passes over whole tiles: no split-K atomics, the same bits every time
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    # tiles cut by a CTA range boundary are summed with fp32 atomics: launches agree to one fp16 rounding
+    for o in outs[1:]:
+        assert ((o.float() - outs[0].float()).abs() <= 2e-3 * outs[0].float().abs() + 1e-6).all()
 
 
 def _exact_w6ax_chunked(capi, xq, sx, w6, wsc, N, n_chunk=2048):

@@ -60,10 +60,24 @@ def main():
     ap.add_argument("--chain", action="store_true",
                     help="realistic producer chain: (residual+)RMSNorm+quant -> qkv, quant -> o, residual+RMSNorm+quant -> gate_up, "
                          "SiLU*up+quant -> down (needs --fuse-gate-up); fp16 side runs rms_norm / silu*mul / matmul")
+    ap.add_argument("--no-fp16", action="store_true", help="skip the fp16 (cuBLAS) side: its weights take 2.7x the memory")
+    ap.add_argument("--clone-layers", action="store_true", help="quantise + pack one layer and clone it (same timing, faster set-up)")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
-    hid, inter, qkv, layers = MODELS[a.model]
-    layers = a.layers or layers
+    results = run_stack(a.model, a.layers, [int(b) for b in a.batches.split(",")], a.fuse_gate_up, a.chain, not a.no_fp16, a.clone_layers)
+    if a.out:
+        os.makedirs(os.path.dirname(a.out), exist_ok=True)
+        with open(a.out, "w") as f:
+            for r in results:
+                f.write(json.dumps(r) + "\n")
+
+
+def run_stack(model, layers=0, batches=(1,), fuse_gate_up=True, chain=True, with_fp16=True, clone_layers=False, verbose=True):
+    """Time one decode step of `layers` decoder layers' linears (see the module docstring); returns one record per batch."""
+    import types
+    a = types.SimpleNamespace(model=model, fuse_gate_up=fuse_gate_up, chain=chain)
+    hid, inter, qkv, nl = MODELS[model]
+    layers = layers or nl
     dev = torch.device("cuda")
     capi.load()
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -72,18 +86,24 @@ def main():
     shapes += [("gate_up", 2 * inter, hid, 6)] if a.fuse_gate_up else [("gate", inter, hid, 6), ("up", inter, hid, 6)]
     shapes += [("down", hid, inter, 8)]
     packed, fp16 = [], []
-    for _ in range(layers):
+    for li in range(layers):
         lw, lf = [], []
-        for name, N, K, xb in shapes:
-            w = (0.02 * torch.randn(N, K, device=dev)).half()
-            w6, ws = capi.quant_pack_w6(w)
+        for si, (name, N, K, xb) in enumerate(shapes):
+            if clone_layers and li > 0:
+                w6, ws = packed[0][si][0].clone(), packed[0][si][1].clone()
+                w = fp16[0][si].clone() if with_fp16 else None
+            else:
+                w = (0.02 * torch.randn(N, K, device=dev)).half()
+                w6, ws = capi.quant_pack_w6(w)
+                if not with_fp16:
+                    w = None
             lw.append((w6, ws, N, K, xb))
             lf.append(w)
         packed.append(lw)
         fp16.append(lf)
     wbytes = sum(N * K * 6 // 8 + N * (K // 128) * 2 for _, N, K, _ in shapes) * layers
     results = []
-    for B in [int(b) for b in a.batches.split(",")]:
+    for B in batches:
         xs = {K: torch.randn(B, K, device=dev).half() for _, _, K, _ in shapes}
         outs = {(N, K): torch.empty(B, N, dtype=torch.float16, device=dev) for _, N, K, _ in shapes}
         wss = {K: capi.new_workspace(B, K) for _, _, K, _ in shapes}
@@ -135,19 +155,18 @@ def main():
                     h = torch.matmul(act, wdn.t(), out=outs[(wdn.shape[0], wdn.shape[1])])
                 return h
 
-        tq, tf = graph_us(run_q), graph_us(run_f)
+        tq = graph_us(run_q)
+        tf = graph_us(run_f) if with_fp16 else None
         rec = {"model": a.model, "layers": layers, "batch": B, "fuse_gate_up": a.fuse_gate_up, "chain": a.chain, "linears_per_layer": len(shapes),
-               "w6ax_us": tq, "w6ax_tok_s": B / tq * 1e6, "fp16_us": tf, "fp16_tok_s": B / tf * 1e6, "speedup_vs_fp16": tf / tq,
+               "w6ax_us": tq, "w6ax_tok_s": B / tq * 1e6, "fp16_us": tf, "fp16_tok_s": B / tf * 1e6 if tf else None,
+               "speedup_vs_fp16": tf / tq if tf else None,
                "weight_gbs": wbytes / tq / 1e3, "hbm_frac": wbytes / tq / 1e3 / hbm,
                "note": ("decoder layer without attention / KV: norms, residuals, SiLU*up and all linears; synthetic weights" if a.chain
                         else "linear stack only (no attention / KV / norms); synthetic weights")}
         results.append(rec)
-        print(json.dumps(rec), flush=True)
-    if a.out:
-        os.makedirs(os.path.dirname(a.out), exist_ok=True)
-        with open(a.out, "w") as f:
-            for r in results:
-                f.write(json.dumps(r) + "\n")
+        if verbose:
+            print(json.dumps(rec), flush=True)
+    return results
 
 
 if __name__ == "__main__":
