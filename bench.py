@@ -271,7 +271,37 @@ def extra_records(capi, layers, fp16_w, dev, xb, hbm_gbs):
         rec["vs_cublas_f16"] = rec["cublas_f16_us"] / rec["w6ax_gemm_us"]
         vs.append(rec)
     extra["vs_cublas"] = vs
+    # BASELINE.json configs[1]: LLaMA-2-7B linear shapes, W6A8, a few M, fused path beside cuBLAS FP16 (the full sweep with
+    # cuBLAS INT8 is tools/sweep.py -> profiles/sweep_r2.md)
+    sw = []
+    for name, N, K in (("qkvo_4096x4096", 4096, 4096), ("gateup_11008x4096", 11008, 4096), ("down_4096x11008", 4096, 11008)):
+        w = (0.02 * torch.randn(N, K, device=dev)).half()
+        ncopy = max(1, min(8, (2 * L2 + N * K * 6 // 8 - 1) // (N * K * 6 // 8)))
+        copies = [capi.quant_pack_w6(w)] + [None] * (ncopy - 1)
+        for i in range(1, ncopy):
+            copies[i] = (copies[0][0].clone(), copies[0][1].clone())
+        for M in (1, 16, 256, 2048):
+            x = torch.randn(M, K, device=dev).half()
+            out = torch.empty(M, N, dtype=torch.float16, device=dev)
+            ws = capi.new_workspace(M, K)
+            t = graph_time_us([lambda c=c: capi.linear_w6ax(x, c[0], c[1], N, 8, ws, capi.ROUND_CUDA, out) for c in copies])
+            tf = graph_time_us([lambda: torch.matmul(x, w.t(), out=out)])
+            sw.append({"layer": name, "M": M, "w6a8_fused_us": t, "cublas_f16_us": tf, "vs_cublas_f16": tf / t,
+                       "tops": 2.0 * M * N * K / t / 1e6})
+        del copies, w
+    extra["llama2_7b_w6a8"] = sw
     return extra
+
+
+def decode_l3_8b_record():
+    """BASELINE.json configs[3]: LLaMA-3-8B, mixed W6A6 / W6A8 (down_proj A8), synthetic weights, all 32 layers' norms,
+    residuals, SiLU*up and linears under one CUDA graph per token step (attention / KV cache excluded), beside the same
+    chain in fp16 (rms_norm / silu / cuBLAS)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import decode_stack
+    recs = decode_stack.run_stack("llama3-8b", 32, [1, 16], True, True, with_fp16=True, clone_layers=True, verbose=False)
+    return [{"batch": r["batch"], "layers": r["layers"], "us_per_step": r["w6ax_us"], "tok_s": r["w6ax_tok_s"], "hbm_frac": r["hbm_frac"],
+             "fp16_us_per_step": r["fp16_us"], "speedup_vs_fp16": r["speedup_vs_fp16"]} for r in recs]
 
 
 def decode_tok_s_record():
@@ -499,6 +529,11 @@ def main():
                                           "norms, residuals, SiLU*up and every linear; attention / KV cache excluded")
         except Exception as e:                       # noqa: BLE001
             extra["decode_tok_s_err"] = str(e)[:200]
+        torch.cuda.empty_cache()
+        try:
+            extra["decode_llama3_8b_mixed"] = decode_l3_8b_record()
+        except Exception as e:                       # noqa: BLE001
+            extra["decode_llama3_8b_err"] = str(e)[:200]
 
     h2d = sum(x.numel() * 2 for x in x_host)
     d2h = sum(y.numel() * 2 for y in y_host)

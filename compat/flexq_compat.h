@@ -39,10 +39,15 @@ typedef FQBMMAOpState (*FQBMMAInitFn_t)(int*, int*, half*, half*, int, int, int,
 typedef void (*FQBMMAExecFn_t)(FQBMMAOpState&, cudaStream_t);
 
 // One pair per activation width.  Init converts the weight planes to W6 tiles once per weight
-// pointer (cached, freed by flexq_compat_release()) and sizes the workspace; Exec is asynchronous.
+// pointer (cached, freed by flexq_compat_release()); Exec is asynchronous and takes the workspace of its stream
+// (one per stream, grown to the problem: no token limit, Execs on different streams never share scratch).
 FQBMMAOpState FQBMMA_W6A6_InitFn(int* X, int* W, half* X_SCALE, half* W_SCALE, int M, int N, int K, half* D, int group_size, bool bias);
 FQBMMAOpState FQBMMA_W6A8_InitFn(int* X, int* W, half* X_SCALE, half* W_SCALE, int M, int N, int K, half* D, int group_size, bool bias);
 void FQBMMA_ExecFn(FQBMMAOpState& state, cudaStream_t stream);
+// The converted tiles are cached by weight pointer (+ N, K).  A caller that repacks a weight in place, or frees it so
+// that the allocator may hand the address to another weight of the same shape, calls flexq_compat_invalidate(W) first;
+// flexq_compat_release() frees everything (converted tiles and the per-stream workspaces).
+void flexq_compat_invalidate(const int* W);
 void flexq_compat_release();
 
 // legacy symbol names (common/base.h:286-308 naming) resolve to the pairs above

@@ -6,6 +6,7 @@ Public surface mirrors the reference's: ``QuantLinear`` / ``UniformAffineQuantiz
 from . import capi  # noqa: F401
 from .quantizer import UniformAffineQuantizer  # noqa: F401
 from .int_linear import QuantLinear  # noqa: F401
-from .int_llama_layer import QuantLlamaMLP  # noqa: F401
+from .int_llama_layer import QuantLlamaAttention, QuantLlamaDecoderLayer, QuantLlamaMLP, quantize_llama  # noqa: F401
 
-__all__ = ["capi", "UniformAffineQuantizer", "QuantLinear", "QuantLlamaMLP"]
+__all__ = ["capi", "UniformAffineQuantizer", "QuantLinear", "QuantLlamaMLP", "QuantLlamaAttention", "QuantLlamaDecoderLayer",
+           "quantize_llama"]

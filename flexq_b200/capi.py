@@ -46,6 +46,7 @@ _SIGNATURES = {
     "flexq_gemm_w6ax": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_gemm_w6ax_groupsums": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "flexq_debug_schedule": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int), _i, ctypes.POINTER(ctypes.c_int)]),
+    "flexq_debug_tile_contributors": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int), _i]),
     "flexq_debug_gemm_trace": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "flexq_linear_w6ax_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_gemm_ref_layout": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
@@ -128,6 +129,26 @@ def ceil4(m: int) -> int:
 # ------------------------------------------------------------------------------------------
 # thin tensor-level wrappers (allocate outputs with torch, call the C ABI on the current stream)
 # ------------------------------------------------------------------------------------------
+_ws_pool: dict = {}
+
+
+def stream_workspace(M: int | None = None, K: int | None = None, device=None) -> torch.Tensor:
+    """The workspace shared by every flexq_b200 call issued on the current stream of `device` (calls on one stream run
+    one after the other, so they can share the GEMM's partial-sum scratch and the quantised-activation staging area; a
+    workspace must not be used by GEMMs running concurrently on different streams).  Grown on demand, zeroed once."""
+    lib = load()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    need = lib.flexq_gemm_workspace_bytes() if M is None else lib.flexq_linear_workspace_bytes(M, K)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_pool.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+        _ws_pool[key] = ws
+    return ws
+
+
 def new_workspace(M: int | None = None, K: int | None = None, device="cuda") -> torch.Tensor:
     lib = load()
     n = lib.flexq_gemm_workspace_bytes() if M is None else lib.flexq_linear_workspace_bytes(M, K)

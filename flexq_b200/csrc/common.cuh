@@ -17,9 +17,10 @@ namespace flexq {
 constexpr int kGroup = FLEXQ_GROUP;          // 128 k-values share one scale
 constexpr int kTileN = 128;                  // weight rows per W6 tile (= UMMA M)
 constexpr int kTileBytes = kTileN * kGroup * 6 / 8;   // 12288
-constexpr int kMaxCtas = 160;                // >= SM count; sizes the split-K slot pool
-constexpr int kSlotFloats = kTileN * 256;    // one partial-tile slot (fp32), M_TILE <= 256
-constexpr size_t kCntBytes = 1024;           // kMaxCtas int32 counters, padded
+constexpr int kMaxCtas = 160;                // >= SM count
+constexpr int kMaxSlots = 3 * kMaxCtas;      // partial-tile slots: two per CTA + one per token tile (gemm_w6ax.cu partial_slot)
+constexpr int kSlotFloats = kTileN * 192;    // one partial-tile slot (fp32), token tile <= 192
+constexpr size_t kCntBytes = 2048;           // kMaxSlots int32 counters, padded
 
 __host__ __device__ inline int ceil4(int m) { return (m + 3) / 4 * 4; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -37,8 +37,8 @@ struct GemmParams {
     const uint8_t* w6;
     __half* D;               // [M][N]
     int32_t* S;              // [M][N][G] (DUMP only)
-    float* slots;            // [kMaxCtas][M_TILE][128] fp32 partial tiles
-    int* cnt;                // [kMaxCtas] group counters
+    float* slots;            // [kMaxSlots][kSlotFloats] fp32 partial tiles, one per cut run (see partial_slot)
+    int* cnt;                // [kMaxSlots] group counters (zero between launches)
     int M, N, K, G;
     int m_tiles, n_tiles;    // tile index = mt * n_tiles + nt: CTAs that run concurrently stream the same weight rows
                              // (one token tile each), so a weight row is fetched from HBM once and hit in L2 by the rest
@@ -67,6 +67,7 @@ struct GemmParams {
 #define FLEXQ_BIASMMA 1
 #endif
 constexpr uint32_t kBiasB = 32u * 255u * 255u;
+constexpr int kMaxListed = 32;   // contributors of a cut tile listed in shared memory (more are walked one by one)
 
 template <int M_TILE, int GP>
 struct Cfg {
@@ -84,8 +85,10 @@ struct Cfg {
     static constexpr int A_COL0 = NAB * ACC_COLS;
     static_assert(NAT >= 2 && NAB * ACC_COLS + NAT * A_COLS <= 512, "TMEM budget");
     // ---- shared memory rings
-    static constexpr int NX = (M_TILE >= 128) ? 4 : 2;             // activation stages
-    static constexpr int NS = (M_TILE >= 128) ? 4 : 3;             // scale stages
+    // activation / scale stages.  Decode tiles: the stages are tiny (8 KB + 1.3 KB) and the last steps of a CTA must not
+    // wait for an activation load issued only when step - NX retired (measured: 1300 cycles of the decode tail)
+    static constexpr int NX = (M_TILE >= 128) ? 4 : (M_TILE <= 16 ? 6 : 4);
+    static constexpr int NS = (M_TILE >= 128) ? 4 : (M_TILE <= 16 ? 6 : 4);
     static constexpr int X_BYTES = GP * M_TILE * 128;              // [GP][M_TILE][128 B], swizzle-128B
     static constexpr int SX_BYTES = GP * M_TILE * 4;               // f32 [GP][M_TILE]
     static constexpr int SW_BYTES = GP * kTileN * 2;               // f16 [GP][128]
@@ -105,7 +108,7 @@ struct Cfg {
     static constexpr int NDONE = 16;                               // "MMAs of step i retired" ring (> NAB, NAT, NX)
     static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
-    static constexpr int OFF_ONES = (OFF_MISC + 16 + 127) / 128 * 128;
+    static constexpr int OFF_ONES = (OFF_MISC + 16 + 4 * kMaxListed + 127) / 128 * 128;   // misc: tmem base, flags, contributor list
     static constexpr int SMEM_BYTES = OFF_ONES + ONES_BYTES + 1024; // + alignment slack
     // epilogue warpgroups.  Measured on B200 (70B shapes, M >= 2048): 3 warpgroups of 64 columns (12 warps, 128 regs)
     // beat 2 x 96 columns (8 warps, 200 regs) by 3-8 % on the 192-token tile -- one more warp per scheduler to
@@ -211,31 +214,61 @@ __host__ __device__ __forceinline__ Sched make_sched(const GemmParams& p, int ct
     return s;
 }
 
-// f(mt, nt, g0, g1) for every maximal run of k-groups [g0, g1) of one tile in this CTA's range, in order
+// f(mt, nt, g0, g1, flags) for every maximal run of k-groups [g0, g1) of one tile in this CTA's range, in order.
+// flags: kSegFirst = the run starts at the start of the CTA's range, kSegRowHead = it starts at unit Ureg of a token
+// tile in the spare region (both matter only for runs that do not cover their whole tile, see partial_slot).
+constexpr int kSegFirst = 1, kSegRowHead = 2;
 template <typename F>
 __host__ __device__ __forceinline__ void walk_segments(const Sched& s, int G, F&& f) {
     for (int idx = s.a; idx < s.b;) {
         const int row = idx / s.L;
         const int rend = (long long)(row + 1) * s.L < (long long)s.b ? (row + 1) * s.L : s.b;
         const int mt = s.mt0 + row * s.mts;
-        for (int u = s.ub + (idx - row * s.L), ue = u + (rend - idx); u < ue;) {
+        for (int u = s.ub + (idx - row * s.L), ue = u + (rend - idx), i = idx; u < ue;) {
             const int nt = u / G, g0 = u - nt * G;
             const int g1 = g0 + (ue - u) < G ? g0 + (ue - u) : G;
-            f(mt, nt, g0, g1);
+            f(mt, nt, g0, g1, (i == s.a ? kSegFirst : 0) | ((s.ub > 0 && i == row * s.L) ? kSegRowHead : 0));
             u += g1 - g0;
+            i += g1 - g0;
         }
         idx = rend;
     }
 }
 
-// slot of the fp32 partial sums of tile (mt, nt): the CTA that owns the tile's first unit
-__host__ __device__ __forceinline__ int tile_slot(const GemmParams& p, int mt, int nt) {
-    const int u0 = nt * p.G;
-    if (u0 < p.Ureg) return mt * p.Pn + unit_owner(u0, p.Ureg, p.Pn);
-    const int Ls = p.n_tiles * p.G - p.Ureg;
-    const long long tot = (long long)p.R * Ls, i0 = (long long)mt * Ls + (u0 - p.Ureg);
-    const int nsp = p.P - p.R * p.Pn;
-    return p.R * p.Pn + (int)(((i0 + 1) * nsp - 1) / tot);
+// Partial sums of a tile that is cut by range boundaries: every contributing run writes its fp32 partial tile to a slot
+// of its own and adds its group count to the tile's counter; whoever completes the count sums the slots in unit order
+// (re-read from the slots, its own included) -- no atomics on data, no zero-initialised scratch, and the same bits whatever the arrival
+// order.  A CTA has at most one cut run at the start and one at the end of its range (slots 2c, 2c + 1); runs starting
+// at Ureg in the spare region are additionally cut by the regular/spare boundary (slot 2P + mt).
+__host__ __device__ __forceinline__ int partial_slot(const GemmParams& p, int cta, int mt, int g0, int flags) {
+    if ((flags & kSegRowHead) && g0 > 0) return 2 * p.P + mt;
+    return 2 * cta + ((flags & kSegFirst) ? 0 : 1);
+}
+
+// g(slot, cta) for the runs that make up tile (mt, nt), in unit order (what the completing CTA walks)
+template <typename Fn>
+__host__ __device__ __forceinline__ void tile_contributors(const GemmParams& p, int mt, int nt, Fn&& g) {
+    const int G = p.G, Umt = p.n_tiles * p.G, t0 = nt * G, t1 = t0 + G;
+    const int Ls = Umt - p.Ureg, nsp = p.P - p.R * p.Pn;
+    for (int u = t0; u < t1;) {
+        int cta, b, flags = 0;             // owner of unit u, end of its range in units of this token tile
+        if (u < p.Ureg) {
+            const int j = unit_owner(u, p.Ureg, p.Pn);
+            cta = mt * p.Pn + j;
+            b = (int)(((long long)(j + 1) * p.Ureg) / p.Pn);
+            if (u == (int)(((long long)j * p.Ureg) / p.Pn)) flags |= kSegFirst;
+        } else {
+            const long long tot = (long long)p.R * Ls, i0 = (long long)mt * Ls + (u - p.Ureg);
+            const int sp = (int)(((i0 + 1) * nsp - 1) / tot);
+            const long long ia = (sp * tot) / nsp, ib = ((sp + 1) * tot) / nsp, rowend = (long long)(mt + 1) * Ls;
+            cta = p.R * p.Pn + sp;
+            b = u + (int)((ib < rowend ? ib : rowend) - i0);
+            if (i0 == ia) flags |= kSegFirst;
+            if (u == p.Ureg) flags |= kSegRowHead;
+        }
+        g(partial_slot(p, cta, mt, u - t0, flags), cta);
+        u = b < t1 ? b : t1;
+    }
 }
 
 // host: fill the decomposition fields of p (n_tiles, m_tiles, G set) for at most max_ctas CTAs
@@ -265,13 +298,24 @@ int debug_schedule(int m_tiles, int n_tiles, int G, int max_ctas, int cta, int* 
     if (n_ctas) *n_ctas = p.P;
     if (cta < 0 || cta >= p.P) return 0;
     int n = 0;
-    walk_segments(make_sched(p, cta), G, [&](int mt, int nt, int g0, int g1) {
+    walk_segments(make_sched(p, cta), G, [&](int mt, int nt, int g0, int g1, int flags) {
         if (n < cap) {
             out[5 * n] = mt; out[5 * n + 1] = nt; out[5 * n + 2] = g0; out[5 * n + 3] = g1;
-            out[5 * n + 4] = (g0 == 0 && g1 == G) ? -1 : tile_slot(p, mt, nt);
+            out[5 * n + 4] = (g0 == 0 && g1 == G) ? -1 : partial_slot(p, cta, mt, g0, flags);
         }
         n++;
     });
+    return n;
+}
+
+// debug / test: the slots the completing CTA sums for tile (mt, nt), in order; returns their number
+int debug_tile_contributors(int m_tiles, int n_tiles, int G, int max_ctas, int mt, int nt, int* slots, int cap) {
+    GemmParams p{};
+    p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.G = G;
+    plan_ctas(p, max_ctas);
+    if (p.whole_rows) return 0;
+    int n = 0;
+    tile_contributors(p, mt, nt, [&](int slot, int) { if (n < cap) slots[n] = slot; n++; });
     return n;
 }
 
@@ -327,7 +371,6 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::NAT; s++) mbar_init(bar_a_full(s), 128);
         for (int s = 0; s < C::NX; s++) mbar_init(bar_x_full(s), 1);
-        for (int s = 0; s < C::NW; s++) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 128); }
         for (int s = 0; s < C::NS; s++) { mbar_init(bar_s_full(s), 1); mbar_init(bar_s_empty(s), C::EPI_THREADS); }
         for (int b = 0; b < C::NAB; b++) mbar_init(bar_acc_empty(b), C::EPI_THREADS);
         for (int i = 0; i < C::NDONE; i++) mbar_init(bar_done(i), 1);
@@ -337,6 +380,42 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         prefetch_tensormap(&tmap_sw);
     }
     const int cw = warp - C::CTRL_WARP0;        // 0 = W producer, 1 and 2 = MMA issuers, 3 = X producer
+    // weight loads of steps [lo, hi) of this CTA (one thread)
+    auto w_produce = [&](const int lo, const int hi) {
+        // weights are read once when there is a single token tile (decode): keep them from
+        // displacing activations/scales in L2; with several token tiles the same weight row is
+        // re-streamed per token tile and should stay resident
+        const uint64_t pol = (p.m_tiles == 1) ? l2_policy_evict_first() : l2_policy_evict_last();
+        int it = 0;
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
+            const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
+            for (int g = g0; g < g1; g += GP, it++) {
+                if (it < lo || it >= hi) continue;
+                const int ng = min(GP, g1 - g);
+                const int s = it % C::NW;
+                mbar_wait_parked(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
+                FQ_TRACE(it, 0);
+                mbar_expect_tx(bar_w_full(s), ng * kTileBytes);
+                if (p.m_tiles == 1) {
+                    bulk_g2s_hint(smem_base + C::OFF_W + s * C::W_BYTES, wsrc + (size_t)g * kTileBytes, ng * kTileBytes, bar_w_full(s), pol);
+                } else {
+                    // re-streamed weights go through tensor-map TMA loads (W6 seen as [bytes/128][128]); measured:
+                    // plain bulk copies never hit in L2 on the second pass, tiled loads do
+                    for (int j = 0; j < ng; j++)
+                        tma_load_2d_hint(smem_base + C::OFF_W + s * C::W_BYTES + j * kTileBytes, &tmap_w, 0,
+                                         (nt * G + g + j) * (kTileBytes / 128), bar_w_full(s), pol);
+                }
+            }
+        });
+    };
+    if (cw == 0 && lane == 0) {
+        // The weight stream starts before the rest of the prologue (TMEM allocation, the other barriers, the CTA-wide
+        // sync): weights are static, the ring is empty and its barriers are this thread's own -- at decode sizes the
+        // prologue is ~0.7 us of a 10 us kernel.
+        for (int s = 0; s < C::NW; s++) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 128); }
+        fence_barrier_init();
+        w_produce(0, C::NW);
+    }
     if (cw == 1) tmem_alloc<512>(smem_u32(&misc[0]));
     if constexpr (C::BIAS) {   // constant operand of the bias MMA, read through the async proxy
         for (int i = threadIdx.x; i < C::ONES_BYTES / 16; i += C::THREADS)
@@ -361,30 +440,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ===================== TMA producer: packed weight tiles =====================
         reg_dealloc<32>();
         if (lane == 0) {
-            // weights are read once when there is a single token tile (decode): keep them from
-            // displacing activations/scales in L2; with several token tiles the same weight row is
-            // re-streamed per token tile and should stay resident
-            const uint64_t pol = (p.m_tiles == 1) ? l2_policy_evict_first() : l2_policy_evict_last();
-            int it = 0;
-            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
-                const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
-                for (int g = g0; g < g1; g += GP, it++) {
-                    const int ng = min(GP, g1 - g);
-                    const int s = it % C::NW;
-                    mbar_wait_parked(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
-                    FQ_TRACE(it, 0);
-                    mbar_expect_tx(bar_w_full(s), ng * kTileBytes);
-                    if (p.m_tiles == 1) {
-                        bulk_g2s_hint(smem_base + C::OFF_W + s * C::W_BYTES, wsrc + (size_t)g * kTileBytes, ng * kTileBytes, bar_w_full(s), pol);
-                    } else {
-                        // re-streamed weights go through tensor-map TMA loads (W6 seen as [bytes/128][128]); measured:
-                        // plain bulk copies never hit in L2 on the second pass, tiled loads do
-                        for (int j = 0; j < ng; j++)
-                            tma_load_2d_hint(smem_base + C::OFF_W + s * C::W_BYTES + j * kTileBytes, &tmap_w, 0,
-                                             (nt * G + g + j) * (kTileBytes / 128), bar_w_full(s), pol);
-                    }
-                }
-            });
+            w_produce(C::NW, 0x7fffffff);
         } else if (TRACE && lane == 1 && blockIdx.x == (p.trace_units >> 16)) {
             // trace builds: an otherwise idle lane watches the "MMAs of step i retired" barriers (event 8)
             const int n = min(sch.b - sch.a, p.trace_units & 0xFFFF);
@@ -401,7 +457,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             asm volatile("griddepcontrol.wait;" ::: "memory");     // activations / scales come from earlier kernels
             const uint64_t pol_x = l2_policy_evict_last();          // every n-tile re-reads the activations: keep them in L2
             int it = 0;
-            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
+            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
                 for (int g = g0; g < g1; g += GP, it++) {
                     {   // [ng][M_TILE][128 B] swizzle-128B tiles, one TMA per k-group; rows >= M are zero-filled
                         const int ng = min(GP, g1 - g);
@@ -438,7 +494,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
             int it = 0;
-            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
+            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
                 for (int g = g0; g < g1; g += GP, it++) {
                     if ((it & 1) != my_parity) continue;
                     const int ng = min(GP, g1 - g);
@@ -497,7 +553,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         asm volatile("" : "+r"(w_thread));
         int it = 0, sw = 0;
         uint32_t w_par = 0;
-        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
             for (int g = g0; g < g1; g += GP, it++) {
                 const int ng = min(GP, g1 - g);
                 const int st = it % C::NAT;
@@ -589,7 +645,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         constexpr bool PREFETCH = (FLEXQ_EPI_PREFETCH != 0) && GP == 1 && ((CPT / CH) % 2 == 0) && !kRearm;
         bool pre = false;
         const int n_steps = sch.b - sch.a;
-        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
             const int n = nt * kTileN + r;
             const int mbase = mt * M_TILE + col0;
             const bool n_ok = n < p.N;
@@ -798,36 +854,79 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         }
                     }
                 } else {
-                    // partial tile: accumulate in the slot owned by the tile's first CTA
-                    const int slot = tile_slot(p, mt, nt);
-                    // slot layout [column][row]; thread-private positions: (col0 + j, r), or in the fragment layout value
-                    // v = k * 16 + 2 * jp + s at (col0 + 8 * jp + fc0 + s, fr0 + 8 * k)
-                    float* sl = p.slots + (size_t)slot * kSlotFloats + (size_t)col0 * kTileN + (C::FRAG ? fc0 * kTileN + fr0 : r);
-                    auto slot_off = [&](int v) { return C::FRAG ? (8 * ((v >> 1) & 7) + (v & 1)) * kTileN + 8 * (v >> 4) : v * kTileN; };
+                    // tile cut by a range boundary: park this run's partial sums in its own slot, thread-linear layout
+                    // [value quad][thread] (coalesced 16-byte accesses), and count its groups on the tile's counter
+                    const int my_slot = partial_slot(p, blockIdx.x, mt, g0, sflags);
+                    int first_slot = my_slot;
+                    if (g0 > 0) {
+                        bool got = false;
+                        tile_contributors(p, mt, nt, [&](int sl_, int) { if (!got) { first_slot = sl_; got = true; } });
+                    }
+                    float4* sl = reinterpret_cast<float4*>(p.slots + (size_t)my_slot * kSlotFloats) + e;
 #pragma unroll
-                    for (int j = 0; j < CPT; j++) atomicAdd(sl + slot_off(j), (j & 1) ? acc[j / 2].y : acc[j / 2].x);
-                    named_bar_sync(1, C::EPI_THREADS);              // every thread's red.adds are issued ...
-                    if (e == 0) {                        // ... and released (cumulatively) by one acq_rel atomic
-                        int old;
-                        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.cnt + slot), "r"(g1 - g0) : "memory");
-                        misc[1] = (old + (g1 - g0) == G) ? 1u : 0u;
+                    for (int j = 0; j < CPT / 4; j++) __stcg(sl + j * C::EPI_THREADS, make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y));
+                    named_bar_sync(1, C::EPI_THREADS);              // every thread's stores are issued ...
+                    if (e == 0) {                        // ... and released by one acq_rel atomic (bar.sync + one thread's
+                        int old;                         // release is the pattern of a cooperative grid sync)
+                        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.cnt + first_slot), "r"(g1 - g0) : "memory");
+                        const bool fin = old + (g1 - g0) == G;
+                        int nl = 0;
+                        if (fin) tile_contributors(p, mt, nt, [&](int sl_, int) { if (nl < kMaxListed) misc[4 + nl] = (uint32_t)sl_; nl++; });
+                        misc[2] = (uint32_t)nl;
+                        misc[1] = fin ? 1u : 0u;
                     }
                     named_bar_sync(1, C::EPI_THREADS);
                     const bool last = misc[1] != 0;
                     if (last) {
-                        // all loads first (independent, in flight together), then zero + store:
-                        // interleaving ld/st on the same addresses serialises ~1 us round trips
+                        // sum the runs in unit order, every one (the own included) from its slot: the accumulator registers
+                        // are reused, a second register tile would not fit.  Small tiles load KC runs at a time so that a
+                        // tile shared by many CTAs (decode) does not pay one L2 round trip per run.
+                        constexpr int V4 = CPT / 4, KC = V4 >= 16 ? 1 : 16 / V4;
+                        const int nl = (int)misc[2];
+                        auto add_run = [&](const float4* v, bool first_run) {
 #pragma unroll
-                        for (int j = 0; j < CPT / 2; j++) acc[j] = make_float2(__ldcg(sl + slot_off(2 * j)), __ldcg(sl + slot_off(2 * j + 1)));
+                            for (int j = 0; j < V4; j++) {
+                                if (first_run) {
+                                    acc[2 * j] = make_float2(v[j].x, v[j].y); acc[2 * j + 1] = make_float2(v[j].z, v[j].w);
+                                } else {
+                                    acc[2 * j].x += v[j].x; acc[2 * j].y += v[j].y; acc[2 * j + 1].x += v[j].z; acc[2 * j + 1].y += v[j].w;
+                                }
+                            }
+                        };
+                        if (nl <= kMaxListed) {
+                            for (int i0 = 0; i0 < nl; i0 += KC) {
+                                float4 v[KC][V4];
+#pragma unroll
+                                for (int c = 0; c < KC; c++) {
+                                    if (i0 + c < nl) {
+                                        const float4* src = reinterpret_cast<const float4*>(p.slots + (size_t)misc[4 + i0 + c] * kSlotFloats) + e;
+#pragma unroll
+                                        for (int j = 0; j < V4; j++) v[c][j] = __ldcg(src + j * C::EPI_THREADS);
+                                    }
+                                }
+#pragma unroll
+                                for (int c = 0; c < KC; c++)
+                                    if (i0 + c < nl) add_run(v[c], i0 + c == 0);
+                            }
+                        } else {
+                            bool started = false;
+                            tile_contributors(p, mt, nt, [&](int sl_, int) {
+                                const float4* src = reinterpret_cast<const float4*>(p.slots + (size_t)sl_ * kSlotFloats) + e;
+                                float4 v[V4];
+#pragma unroll
+                                for (int j = 0; j < V4; j++) v[j] = __ldcg(src + j * C::EPI_THREADS);
+                                add_run(v, !started);
+                                started = true;
+                            });
+                        }
 #pragma unroll
                         for (int j = 0; j < CPT; j++) {
-                            __stcg(sl + slot_off(j), 0.f);
                             const int m = C::FRAG ? mbase + 8 * ((j >> 1) & 7) + fc0 + (j & 1) : mbase + j;
                             const int n2 = C::FRAG ? nt * kTileN + fr0 + 8 * (j >> 4) : n;
                             const float vsum = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
                             if (n2 < p.N && m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2, __half_as_ushort(__float2half_rn(vsum)));
                         }
-                        if (e == 0) p.cnt[slot] = 0;
+                        if (e == 0) p.cnt[first_slot] = 0;
                     }
                     named_bar_sync(1, C::EPI_THREADS);              // flag word is reused by the next partial segment
                 }

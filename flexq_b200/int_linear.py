@@ -80,12 +80,8 @@ class QuantLinear(nn.Module):
         return self.w6, self.w_scale
 
     def _get_workspace(self, M: int, device) -> torch.Tensor:
-        need = capi.load().flexq_linear_workspace_bytes(M, self.in_features)
-        ws = self._workspace
-        if ws is None or ws.numel() < need or ws.device != device:
-            ws = torch.zeros(need, dtype=torch.uint8, device=device)
-            self._workspace = ws
-        return ws
+        # one workspace per (device, stream), shared by all modules: the partial-sum scratch alone is ~47 MB
+        return capi.stream_workspace(M, self.in_features, device)
 
     # ---- forward ----------------------------------------------------------------------------
     def forward(self, input: torch.Tensor):

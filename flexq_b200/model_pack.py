@@ -143,10 +143,8 @@ class PackedLinear(nn.Module):
             raise capi.FlexQError("PackedLinear needs CUDA tensors (no CPU fallback)")
         lead = x.shape[:-1]
         x2 = x.reshape(-1, self.in_features).half().contiguous()
-        need = capi.load().flexq_linear_workspace_bytes(x2.shape[0], self.in_features)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.zeros(need, dtype=torch.uint8, device=x.device)
-        y = capi.linear_w6ax(x2, self.w6, self.w_scale, self.out_features, self.x_bits, self._ws, self.act_round)
+        ws = capi.stream_workspace(x2.shape[0], self.in_features, x.device)
+        y = capi.linear_w6ax(x2, self.w6, self.w_scale, self.out_features, self.x_bits, ws, self.act_round)
         if self.bias is not None:
             y = y + self.bias.to(y.dtype)
         return y.reshape(*lead, self.out_features).to(x.dtype)

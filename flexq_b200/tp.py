@@ -153,10 +153,7 @@ class TPLinearW6Ax:
         return self
 
     def workspace(self, M: int) -> torch.Tensor:
-        need = capi.load().flexq_linear_workspace_bytes(M, self.K)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.zeros(need, dtype=torch.uint8, device=self.w6.device)
-        return self._ws
+        return capi.stream_workspace(M, self.K, self.w6.device)       # one per (device, stream), shared by all layers
 
     def forward(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         M = x.shape[0]
