@@ -46,7 +46,6 @@ _SIGNATURES = {
     "flexq_gemm_w6ax": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_gemm_w6ax_groupsums": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "flexq_debug_schedule": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int), _i, ctypes.POINTER(ctypes.c_int)]),
-    "flexq_debug_tile_contributors": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int), _i]),
     "flexq_debug_gemm_trace": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "flexq_linear_w6ax_f16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_gemm_ref_layout": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),

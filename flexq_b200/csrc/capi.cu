@@ -7,7 +7,6 @@ int quant_act_native(const __half*, int8_t*, float*, int, int, int, int, cudaStr
 int quant_act_planes(const __half*, uint32_t*, __half*, int, int, int, cudaStream_t);
 int quant_act_f32(const float*, int8_t*, float*, int, int, int, cudaStream_t);
 int debug_schedule(int, int, int, int, int, int*, int, int*);
-int debug_tile_contributors(int, int, int, int, int, int, int*, int);
 template <typename T> int pack_w6(const T*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int quant_pack_w6(const T*, uint8_t*, __half*, int, int, cudaStream_t);
 int unpack_w6(const uint8_t*, int8_t*, int, int, cudaStream_t);
@@ -50,7 +49,7 @@ size_t flexq_w6_packed_bytes(int N, int K) { return (size_t)ceil_div(N, kTileN) 
 size_t flexq_planes_bytes(int R, int K, int bits) { return (size_t)R * K / 8 * bits; }
 int flexq_sx_ld(int M) { return ceil4(M); }
 size_t flexq_xscale_ref_halves(int M, int K) { return (size_t)(K / kGroup) * 2 * ceil4(M); }
-size_t flexq_gemm_workspace_bytes(void) { return kCntBytes + (size_t)kMaxSlots * kSlotFloats * sizeof(float); }
+size_t flexq_gemm_workspace_bytes(void) { return kGemmWorkspaceBytes; }
 size_t flexq_linear_workspace_bytes(int M, int K) {
     return flexq_gemm_workspace_bytes() + align_up((size_t)M * K, 256) + align_up((size_t)(K / kGroup) * ceil4(M) * sizeof(float), 256);
 }
@@ -74,10 +73,6 @@ int flexq_quant_act(const void* x, int8_t* xq, float* sx, int M, int K, int bits
 
 int flexq_debug_schedule(int m_tiles, int n_tiles, int groups, int max_ctas, int cta, int* segments, int cap, int* n_ctas) {
     return debug_schedule(m_tiles, n_tiles, groups, max_ctas, cta, segments, cap, n_ctas);
-}
-
-int flexq_debug_tile_contributors(int m_tiles, int n_tiles, int groups, int max_ctas, int mt, int nt, int* slots, int cap) {
-    return debug_tile_contributors(m_tiles, n_tiles, groups, max_ctas, mt, nt, slots, cap);
 }
 
 int flexq_quant_act_f32(const float* x, int8_t* xq, float* sx, int M, int K, int bits, void* stream) {

@@ -18,9 +18,16 @@ constexpr int kGroup = FLEXQ_GROUP;          // 128 k-values share one scale
 constexpr int kTileN = 128;                  // weight rows per W6 tile (= UMMA M)
 constexpr int kTileBytes = kTileN * kGroup * 6 / 8;   // 12288
 constexpr int kMaxCtas = 160;                // >= SM count
-constexpr int kMaxSlots = 3 * kMaxCtas;      // partial-tile slots: two per CTA + one per token tile (gemm_w6ax.cu partial_slot)
-constexpr int kSlotFloats = kTileN * 192;    // one partial-tile slot (fp32), token tile <= 192
-constexpr size_t kCntBytes = 2048;           // kMaxSlots int32 counters, padded
+constexpr int kSlotFloats = kTileN * 192;    // one parked partial tile (fp32), token tile <= 192
+// Split-K scratch (gemm_w6ax.cu).  One 256-byte record per cut tile, indexed by the CTA that owns the tile's first unit
+// ({groups arrived | arrival count << 16, groups parked, -, -, slot ids of the parked runs}), one bump counter, then the
+// fp32 tiles: kMaxCtas accumulation slots (reduction variant: zero between launches) and a pool of kSlotPool parking
+// slots (hand-off variant: a launch parks at most 2 runs per CTA plus one per token tile, < kSlotPool).
+constexpr int kRecInts = 64;
+constexpr int kMaxParked = kRecInts - 4;     // runs one tile can collect before its last contributor arrives
+constexpr int kSlotPool = 448;
+constexpr size_t kCntBytes = (size_t)(kMaxCtas * kRecInts + 64) * 4;   // records + bump counter, 256-byte multiple
+constexpr size_t kGemmWorkspaceBytes = kCntBytes + (size_t)(kMaxCtas + kSlotPool) * kSlotFloats * sizeof(float);
 
 __host__ __device__ inline int ceil4(int m) { return (m + 3) / 4 * 4; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -114,6 +121,18 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
     uint32_t spins = 0;
     while (!mbar_try_wait_parked(bar, parity)) {
         if (++spins > (1u << 22)) __trap();          // >= 60 ms even if the hint is ignored, <= 9 s if honoured
+    }
+}
+
+// ... and for producers of the compute-bound tiles, which run many steps ahead of a ~0.5 us step: the hinted try_wait
+// above wakes on every barrier event of the CTA (measured 11 polls of 7 instructions per step and producer -- 6 % of
+// the issue slots of the four schedulers the epilogue needs); a plain timed sleep between polls leaves two or three
+template <uint32_t NS>
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        asm volatile("nanosleep.u32 %0;" ::"n"(NS));
+        if (++spins > (1u << 24)) __trap();
     }
 }
 

@@ -37,8 +37,9 @@ struct GemmParams {
     const uint8_t* w6;
     __half* D;               // [M][N]
     int32_t* S;              // [M][N][G] (DUMP only)
-    float* slots;            // [kMaxSlots][kSlotFloats] fp32 partial tiles, one per cut run (see partial_slot)
-    int* cnt;                // [kMaxSlots] group counters (zero between launches)
+    float* slots;            // [kMaxCtas + kSlotPool][kSlotFloats] fp32 tiles: accumulation slots, then the parking pool
+    int* cnt;                // [kMaxCtas][kRecInts] cut-tile records + the pool's bump counter (all zero between launches
+                             // except the bump counter)
     int M, N, K, G;
     int m_tiles, n_tiles;    // tile index = mt * n_tiles + nt: CTAs that run concurrently stream the same weight rows
                              // (one token tile each), so a weight row is fetched from HBM once and hit in L2 by the rest
@@ -67,7 +68,6 @@ struct GemmParams {
 #define FLEXQ_BIASMMA 1
 #endif
 constexpr uint32_t kBiasB = 32u * 255u * 255u;
-constexpr int kMaxListed = 32;   // contributors of a cut tile listed in shared memory (more are walked one by one)
 
 template <int M_TILE, int GP>
 struct Cfg {
@@ -85,10 +85,14 @@ struct Cfg {
     static constexpr int A_COL0 = NAB * ACC_COLS;
     static_assert(NAT >= 2 && NAB * ACC_COLS + NAT * A_COLS <= 512, "TMEM budget");
     // ---- shared memory rings
-    // activation / scale stages.  Decode tiles: the stages are tiny (8 KB + 1.3 KB) and the last steps of a CTA must not
-    // wait for an activation load issued only when step - NX retired (measured: 1300 cycles of the decode tail)
-    static constexpr int NX = (M_TILE >= 128) ? 4 : (M_TILE <= 16 ? 6 : 4);
-    static constexpr int NS = (M_TILE >= 128) ? 4 : (M_TILE <= 16 ? 6 : 4);
+    // activation / scale stages.  Decode tiles: the stages are small (8 KB + 1.3 KB at 16 tokens) but their loads queue
+    // behind the saturated weight stream (measured 3000-5000 cycles from issue to arrival, two to three steps): with two
+    // stages every MMA waited for its activations, the TMEM weight stages and then the weight ring backed up behind it
+#ifndef FLEXQ_NX_DECODE
+#define FLEXQ_NX_DECODE 6
+#endif
+    static constexpr int NX = (M_TILE >= 128) ? 4 : (M_TILE <= 16 ? FLEXQ_NX_DECODE : 4);
+    static constexpr int NS = (M_TILE >= 128) ? 4 : (M_TILE <= 16 ? FLEXQ_NX_DECODE : 4);
     static constexpr int X_BYTES = GP * M_TILE * 128;              // [GP][M_TILE][128 B], swizzle-128B
     static constexpr int SX_BYTES = GP * M_TILE * 4;               // f32 [GP][M_TILE]
     static constexpr int SW_BYTES = GP * kTileN * 2;               // f16 [GP][128]
@@ -108,7 +112,7 @@ struct Cfg {
     static constexpr int NDONE = 16;                               // "MMAs of step i retired" ring (> NAB, NAT, NX)
     static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE;
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
-    static constexpr int OFF_ONES = (OFF_MISC + 16 + 4 * kMaxListed + 127) / 128 * 128;   // misc: tmem base, flags, contributor list
+    static constexpr int OFF_ONES = (OFF_MISC + 16 + 4 * kMaxParked + 127) / 128 * 128;   // misc: tmem base, flags, parked slot ids
     static constexpr int SMEM_BYTES = OFF_ONES + ONES_BYTES + 1024; // + alignment slack
     // epilogue warpgroups.  Measured on B200 (70B shapes, M >= 2048): 3 warpgroups of 64 columns (12 warps, 128 regs)
     // beat 2 x 96 columns (8 warps, 200 regs) by 3-8 % on the 192-token tile -- one more warp per scheduler to
@@ -167,6 +171,9 @@ constexpr bool kRearm = FLEXQ_REARM != 0;
 #define FLEXQ_ISSUER_WAITS_SCALES 1
 #endif
 constexpr bool kIssuerWaitsScales = FLEXQ_ISSUER_WAITS_SCALES != 0;
+#ifndef FLEXQ_FIXUP_HANDOFF
+#define FLEXQ_FIXUP_HANDOFF 1
+#endif
 #ifndef FLEXQ_EPI_PREFETCH
 #define FLEXQ_EPI_PREFETCH 0
 #endif
@@ -214,61 +221,31 @@ __host__ __device__ __forceinline__ Sched make_sched(const GemmParams& p, int ct
     return s;
 }
 
-// f(mt, nt, g0, g1, flags) for every maximal run of k-groups [g0, g1) of one tile in this CTA's range, in order.
-// flags: kSegFirst = the run starts at the start of the CTA's range, kSegRowHead = it starts at unit Ureg of a token
-// tile in the spare region (both matter only for runs that do not cover their whole tile, see partial_slot).
-constexpr int kSegFirst = 1, kSegRowHead = 2;
+// f(mt, nt, g0, g1) for every maximal run of k-groups [g0, g1) of one tile in this CTA's range, in order
 template <typename F>
 __host__ __device__ __forceinline__ void walk_segments(const Sched& s, int G, F&& f) {
     for (int idx = s.a; idx < s.b;) {
         const int row = idx / s.L;
         const int rend = (long long)(row + 1) * s.L < (long long)s.b ? (row + 1) * s.L : s.b;
         const int mt = s.mt0 + row * s.mts;
-        for (int u = s.ub + (idx - row * s.L), ue = u + (rend - idx), i = idx; u < ue;) {
+        for (int u = s.ub + (idx - row * s.L), ue = u + (rend - idx); u < ue;) {
             const int nt = u / G, g0 = u - nt * G;
             const int g1 = g0 + (ue - u) < G ? g0 + (ue - u) : G;
-            f(mt, nt, g0, g1, (i == s.a ? kSegFirst : 0) | ((s.ub > 0 && i == row * s.L) ? kSegRowHead : 0));
+            f(mt, nt, g0, g1);
             u += g1 - g0;
-            i += g1 - g0;
         }
         idx = rend;
     }
 }
 
-// Partial sums of a tile that is cut by range boundaries: every contributing run writes its fp32 partial tile to a slot
-// of its own and adds its group count to the tile's counter; whoever completes the count sums the slots in unit order
-// (re-read from the slots, its own included) -- no atomics on data, no zero-initialised scratch, and the same bits whatever the arrival
-// order.  A CTA has at most one cut run at the start and one at the end of its range (slots 2c, 2c + 1); runs starting
-// at Ureg in the spare region are additionally cut by the regular/spare boundary (slot 2P + mt).
-__host__ __device__ __forceinline__ int partial_slot(const GemmParams& p, int cta, int mt, int g0, int flags) {
-    if ((flags & kSegRowHead) && g0 > 0) return 2 * p.P + mt;
-    return 2 * cta + ((flags & kSegFirst) ? 0 : 1);
-}
-
-// g(slot, cta) for the runs that make up tile (mt, nt), in unit order (what the completing CTA walks)
-template <typename Fn>
-__host__ __device__ __forceinline__ void tile_contributors(const GemmParams& p, int mt, int nt, Fn&& g) {
-    const int G = p.G, Umt = p.n_tiles * p.G, t0 = nt * G, t1 = t0 + G;
-    const int Ls = Umt - p.Ureg, nsp = p.P - p.R * p.Pn;
-    for (int u = t0; u < t1;) {
-        int cta, b, flags = 0;             // owner of unit u, end of its range in units of this token tile
-        if (u < p.Ureg) {
-            const int j = unit_owner(u, p.Ureg, p.Pn);
-            cta = mt * p.Pn + j;
-            b = (int)(((long long)(j + 1) * p.Ureg) / p.Pn);
-            if (u == (int)(((long long)j * p.Ureg) / p.Pn)) flags |= kSegFirst;
-        } else {
-            const long long tot = (long long)p.R * Ls, i0 = (long long)mt * Ls + (u - p.Ureg);
-            const int sp = (int)(((i0 + 1) * nsp - 1) / tot);
-            const long long ia = (sp * tot) / nsp, ib = ((sp + 1) * tot) / nsp, rowend = (long long)(mt + 1) * Ls;
-            cta = p.R * p.Pn + sp;
-            b = u + (int)((ib < rowend ? ib : rowend) - i0);
-            if (i0 == ia) flags |= kSegFirst;
-            if (u == p.Ureg) flags |= kSegRowHead;
-        }
-        g(partial_slot(p, cta, mt, u - t0, flags), cta);
-        u = b < t1 ? b : t1;
-    }
+// slot of the fp32 partial sums of tile (mt, nt): the CTA that owns the tile's first unit
+__host__ __device__ __forceinline__ int tile_slot(const GemmParams& p, int mt, int nt) {
+    const int u0 = nt * p.G;
+    if (u0 < p.Ureg) return mt * p.Pn + unit_owner(u0, p.Ureg, p.Pn);
+    const int Ls = p.n_tiles * p.G - p.Ureg;
+    const long long tot = (long long)p.R * Ls, i0 = (long long)mt * Ls + (u0 - p.Ureg);
+    const int nsp = p.P - p.R * p.Pn;
+    return p.R * p.Pn + (int)(((i0 + 1) * nsp - 1) / tot);
 }
 
 // host: fill the decomposition fields of p (n_tiles, m_tiles, G set) for at most max_ctas CTAs
@@ -282,6 +259,26 @@ static void plan_ctas(GemmParams& p, int max_ctas) {
     p.R = p.m_tiles;
     p.Pn = max_ctas / p.R;
     if (p.Pn > Umt) p.Pn = (int)Umt;                                      // at least one unit per CTA
+    // a cut tile collects at most kMaxParked parked runs: ranges of >= G/32 units keep a tile within 34 CTAs (only
+    // problems far smaller than the machine are affected)
+    const int min_units = (p.G + 31) / 32;
+    if (p.Pn > Umt / min_units) {
+        p.Pn = (int)(Umt / min_units) > 0 ? (int)(Umt / min_units) : 1;
+        p.P = p.R * p.Pn; p.Ureg = (int)Umt;
+        return;
+    }
+    // Small problems (fewer n-tiles than columns): when a whole number C of columns per n-tile keeps >= 80 % of the
+    // CTAs busy, cut every tile into exactly C runs.  Every CTA then walks one run of one tile -- one partial-tile
+    // fix-up per CTA instead of two (a range that straddles a tile boundary ends one tile and starts another), and the
+    // fix-up is the serial tail of a kernel that is only a few microseconds long.
+    static const int align_pct = [] { const char* e = getenv("FLEXQ_ALIGN_PCT"); return e ? atoi(e) : 80; }();
+    if (p.Pn >= p.n_tiles && p.Pn < Umt) {
+        const int aligned = p.Pn / p.n_tiles * p.n_tiles;
+        if ((long long)aligned * p.R * 100 >= (long long)max_ctas * align_pct) {
+            p.Pn = aligned; p.P = p.R * p.Pn; p.Ureg = (int)Umt;
+            return;
+        }
+    }
     int spare = p.Pn < Umt ? max_ctas - p.R * p.Pn : 0;
     p.P = p.R * p.Pn + spare;
     p.Ureg = spare ? (int)((Umt * p.R * p.Pn + p.P / 2) / p.P) : (int)Umt;
@@ -298,24 +295,13 @@ int debug_schedule(int m_tiles, int n_tiles, int G, int max_ctas, int cta, int* 
     if (n_ctas) *n_ctas = p.P;
     if (cta < 0 || cta >= p.P) return 0;
     int n = 0;
-    walk_segments(make_sched(p, cta), G, [&](int mt, int nt, int g0, int g1, int flags) {
+    walk_segments(make_sched(p, cta), G, [&](int mt, int nt, int g0, int g1) {
         if (n < cap) {
             out[5 * n] = mt; out[5 * n + 1] = nt; out[5 * n + 2] = g0; out[5 * n + 3] = g1;
-            out[5 * n + 4] = (g0 == 0 && g1 == G) ? -1 : partial_slot(p, cta, mt, g0, flags);
+            out[5 * n + 4] = (g0 == 0 && g1 == G) ? -1 : tile_slot(p, mt, nt);
         }
         n++;
     });
-    return n;
-}
-
-// debug / test: the slots the completing CTA sums for tile (mt, nt), in order; returns their number
-int debug_tile_contributors(int m_tiles, int n_tiles, int G, int max_ctas, int mt, int nt, int* slots, int cap) {
-    GemmParams p{};
-    p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.G = G;
-    plan_ctas(p, max_ctas);
-    if (p.whole_rows) return 0;
-    int n = 0;
-    tile_contributors(p, mt, nt, [&](int slot, int) { if (n < cap) slots[n] = slot; n++; });
     return n;
 }
 
@@ -336,6 +322,10 @@ __global__ void __launch_bounds__(Cfg<M_TILE, GP>::THREADS, 1)
 w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_sx,
                  const __grid_constant__ CUtensorMap tmap_sw, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
     using C = Cfg<M_TILE, GP>;
+    // how tiles cut by a range boundary are summed (see the epilogue): parked partial tiles for the 192-token tile
+    // (contributors arrive far apart: measured 2-11 % faster at M >= 512), shared-slot reductions for the smaller
+    // tiles, whose contributors finish together (hand-off 5-65 % slower there: the completing CTA waits for the rest)
+    constexpr bool kHandoff = (FLEXQ_FIXUP_HANDOFF != 0) && M_TILE == 192;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -380,6 +370,13 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         prefetch_tensormap(&tmap_sw);
     }
     const int cw = warp - C::CTRL_WARP0;        // 0 = W producer, 1 and 2 = MMA issuers, 3 = X producer
+#ifndef FLEXQ_PRODUCER_SLEEP_NS
+#define FLEXQ_PRODUCER_SLEEP_NS 0
+#endif
+    auto producer_wait = [&](const uint32_t bar, const uint32_t parity) {
+        if constexpr (M_TILE >= 128 && FLEXQ_PRODUCER_SLEEP_NS > 0) mbar_wait_sleepy<FLEXQ_PRODUCER_SLEEP_NS>(bar, parity);
+        else mbar_wait_parked(bar, parity);
+    };
     // weight loads of steps [lo, hi) of this CTA (one thread)
     auto w_produce = [&](const int lo, const int hi) {
         // weights are read once when there is a single token tile (decode): keep them from
@@ -387,13 +384,14 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // re-streamed per token tile and should stay resident
         const uint64_t pol = (p.m_tiles == 1) ? l2_policy_evict_first() : l2_policy_evict_last();
         int it = 0;
-        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             const uint8_t* wsrc = p.w6 + ((size_t)nt * G) * kTileBytes;
             for (int g = g0; g < g1; g += GP, it++) {
-                if (it < lo || it >= hi) continue;
+                if (it < lo) continue;
+                if (it >= hi) return;
                 const int ng = min(GP, g1 - g);
                 const int s = it % C::NW;
-                mbar_wait_parked(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
+                producer_wait(bar_w_empty(s), ((it / C::NW) & 1) ^ 1);
                 FQ_TRACE(it, 0);
                 mbar_expect_tx(bar_w_full(s), ng * kTileBytes);
                 if (p.m_tiles == 1) {
@@ -408,10 +406,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         });
     };
-    if (cw == 0 && lane == 0) {
+    if (warp == C::CTRL_WARP0 && lane == 0) {
         // The weight stream starts before the rest of the prologue (TMEM allocation, the other barriers, the CTA-wide
         // sync): weights are static, the ring is empty and its barriers are this thread's own -- at decode sizes the
-        // prologue is ~0.7 us of a 10 us kernel.
+        // prologue is ~0.5 us of a 6-12 us kernel.
         for (int s = 0; s < C::NW; s++) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 128); }
         fence_barrier_init();
         w_produce(0, C::NW);
@@ -457,12 +455,12 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             asm volatile("griddepcontrol.wait;" ::: "memory");     // activations / scales come from earlier kernels
             const uint64_t pol_x = l2_policy_evict_last();          // every n-tile re-reads the activations: keep them in L2
             int it = 0;
-            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
+            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
                 for (int g = g0; g < g1; g += GP, it++) {
                     {   // [ng][M_TILE][128 B] swizzle-128B tiles, one TMA per k-group; rows >= M are zero-filled
                         const int ng = min(GP, g1 - g);
                         const int s = it % C::NX;
-                        if (it >= C::NX) mbar_wait_parked(bar_done(it - C::NX), done_parity(it - C::NX));
+                        if (it >= C::NX) producer_wait(bar_done(it - C::NX), done_parity(it - C::NX));
                         FQ_TRACE(it, 9);
                         mbar_expect_tx(bar_x_full(s), ng * (M_TILE * 128));
                         for (int j = 0; j < ng; j++)
@@ -472,7 +470,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (!DUMP) {   // sx[g..g+GP][m0..] (f32) and w_scale[g..g+GP][n0..] (f16)
                         const int s = it % C::NS;
                         const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
-                        mbar_wait_parked(bar_s_empty(s), ((it / C::NS) & 1) ^ 1);
+                        producer_wait(bar_s_empty(s), ((it / C::NS) & 1) ^ 1);
                         mbar_expect_tx(bar_s_full(s), C::S_BYTES);
                         tma_load_2d(dst, &tmap_sx, mt * M_TILE, g, bar_s_full(s));
                         tma_load_2d(dst + C::SX_BYTES, &tmap_sw, nt * kTileN, g, bar_s_full(s));
@@ -494,7 +492,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         {
             constexpr uint32_t idesc = umma_idesc_i8(kTileN, M_TILE);
             int it = 0;
-            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
+            walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
                 for (int g = g0; g < g1; g += GP, it++) {
                     if ((it & 1) != my_parity) continue;
                     const int ng = min(GP, g1 - g);
@@ -553,7 +551,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         asm volatile("" : "+r"(w_thread));
         int it = 0, sw = 0;
         uint32_t w_par = 0;
-        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             for (int g = g0; g < g1; g += GP, it++) {
                 const int ng = min(GP, g1 - g);
                 const int st = it % C::NAT;
@@ -645,7 +643,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         constexpr bool PREFETCH = (FLEXQ_EPI_PREFETCH != 0) && GP == 1 && ((CPT / CH) % 2 == 0) && !kRearm;
         bool pre = false;
         const int n_steps = sch.b - sch.a;
-        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1, const int sflags) {
+        walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             const int n = nt * kTileN + r;
             const int mbase = mt * M_TILE + col0;
             const bool n_ok = n < p.N;
@@ -854,70 +852,120 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         }
                     }
                 } else {
-                    // tile cut by a range boundary: park this run's partial sums in its own slot, thread-linear layout
-                    // [value quad][thread] (coalesced 16-byte accesses), and count its groups on the tile's counter
-                    const int my_slot = partial_slot(p, blockIdx.x, mt, g0, sflags);
-                    int first_slot = my_slot;
-                    if (g0 > 0) {
-                        bool got = false;
-                        tile_contributors(p, mt, nt, [&](int sl_, int) { if (!got) { first_slot = sl_; got = true; } });
-                    }
-                    float4* sl = reinterpret_cast<float4*>(p.slots + (size_t)my_slot * kSlotFloats) + e;
+                    if constexpr (!kHandoff) {
+                    // Tile cut by a range boundary, reduction variant: every contributor adds its fp32 partial tile into
+                    // the slot of the CTA that owns the tile's first unit with 16-byte vector reductions (thread-linear
+                    // layout, a warp covers 512 contiguous bytes) and counts its groups; the one that completes the
+                    // count loads the sum, re-zeroes the slot and writes D.
+                    const int slot = tile_slot(p, mt, nt);
+                    int* rec = p.cnt + (size_t)slot * kRecInts;
+                    float4* sl = reinterpret_cast<float4*>(p.slots + (size_t)slot * kSlotFloats) + e;
 #pragma unroll
-                    for (int j = 0; j < CPT / 4; j++) __stcg(sl + j * C::EPI_THREADS, make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y));
-                    named_bar_sync(1, C::EPI_THREADS);              // every thread's stores are issued ...
-                    if (e == 0) {                        // ... and released by one acq_rel atomic (bar.sync + one thread's
-                        int old;                         // release is the pattern of a cooperative grid sync)
-                        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p.cnt + first_slot), "r"(g1 - g0) : "memory");
-                        const bool fin = old + (g1 - g0) == G;
-                        int nl = 0;
-                        if (fin) tile_contributors(p, mt, nt, [&](int sl_, int) { if (nl < kMaxListed) misc[4 + nl] = (uint32_t)sl_; nl++; });
-                        misc[2] = (uint32_t)nl;
-                        misc[1] = fin ? 1u : 0u;
+                    for (int j = 0; j < CPT / 4; j++)
+                        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(sl + j * C::EPI_THREADS), "f"(acc[2 * j].x),
+                                     "f"(acc[2 * j].y), "f"(acc[2 * j + 1].x), "f"(acc[2 * j + 1].y)
+                                     : "memory");
+                    named_bar_sync(1, C::EPI_THREADS);              // every thread's reductions are issued ...
+                    if (e == 0) {                        // ... and released (cumulatively) by one acq_rel atomic
+                        int old;
+                        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(rec), "r"(g1 - g0) : "memory");
+                        misc[1] = (old + (g1 - g0) == G) ? 1u : 0u;
                     }
                     named_bar_sync(1, C::EPI_THREADS);
                     const bool last = misc[1] != 0;
+                    if (e == 0) FQ_TRACE(it - 1, 14);
                     if (last) {
-                        // sum the runs in unit order, every one (the own included) from its slot: the accumulator registers
-                        // are reused, a second register tile would not fit.  Small tiles load KC runs at a time so that a
-                        // tile shared by many CTAs (decode) does not pay one L2 round trip per run.
-                        constexpr int V4 = CPT / 4, KC = V4 >= 16 ? 1 : 16 / V4;
-                        const int nl = (int)misc[2];
-                        auto add_run = [&](const float4* v, bool first_run) {
+                        // all loads first (independent, in flight together), then zero + store
 #pragma unroll
-                            for (int j = 0; j < V4; j++) {
-                                if (first_run) {
-                                    acc[2 * j] = make_float2(v[j].x, v[j].y); acc[2 * j + 1] = make_float2(v[j].z, v[j].w);
-                                } else {
-                                    acc[2 * j].x += v[j].x; acc[2 * j].y += v[j].y; acc[2 * j + 1].x += v[j].z; acc[2 * j + 1].y += v[j].w;
+                        for (int j = 0; j < CPT / 4; j++) {
+                            const float4 v = __ldcg(sl + j * C::EPI_THREADS);
+                            acc[2 * j] = make_float2(v.x, v.y);
+                            acc[2 * j + 1] = make_float2(v.z, v.w);
+                        }
+                        if (TRACE && e == 0 && acc[0].x != 12345.f) FQ_TRACE(it - 1, 15);      // depends on the first load
+#pragma unroll
+                        for (int j = 0; j < CPT / 4; j++) __stcg(sl + j * C::EPI_THREADS, make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+                        for (int j = 0; j < CPT; j++) {
+                            const int m = C::FRAG ? mbase + 8 * ((j >> 1) & 7) + fc0 + (j & 1) : mbase + j;
+                            const int n2 = C::FRAG ? nt * kTileN + fr0 + 8 * (j >> 4) : n;
+                            const float vsum = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
+                            if (n2 < p.N && m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2, __half_as_ushort(__float2half_rn(vsum)));
+                        }
+                        if (e == 0) rec[0] = 0;
+                    }
+                    named_bar_sync(1, C::EPI_THREADS);              // flag word is reused by the next partial segment
+                    } else {
+                    // Tile cut by a range boundary ("hand-off"): every contributor announces its groups on the tile's
+                    // record; all but the one that completes the count park their fp32 partial tile in a pool slot (plain
+                    // coalesced 16-byte stores, thread-linear [value quad][thread]: every contributor runs the same
+                    // configuration, so a thread meets its own elements again) and publish the slot; the completing CTA
+                    // keeps its partial in registers, waits until everything announced is parked (normally long done:
+                    // the other contributors met this tile at the start of their ranges), adds the parked tiles and
+                    // writes D.  Against fp32 reductions into a shared slot (red.add, then load + zero by the finisher)
+                    // this moves a third of the bytes through L2 and needs no zeroed scratch; with two contributors --
+                    // every cut tile of a prefill-sized problem -- the sum is the same bits whoever finishes.
+                    int* rec = p.cnt + (size_t)tile_slot(p, mt, nt) * kRecInts;
+                    const int ngr = g1 - g0;
+                    if (e == 0) {
+                        // one round trip: groups arrived (low half) and arrival index (high half) in one word, and a pool
+                        // slot drawn at the same time (the completing CTA's draw is simply not used)
+                        int old, draw;
+                        asm volatile("atom.add.relaxed.gpu.global.s32 %0, [%2], %4;\n\tatom.add.relaxed.gpu.global.s32 %1, [%3], 1;"
+                                     : "=r"(old), "=r"(draw) : "l"(rec), "l"(p.cnt + kMaxCtas * kRecInts), "r"(ngr + (1 << 16)) : "memory");
+                        misc[1] = ((old & 0xFFFF) + ngr == G) ? 1u : 0u;
+                        misc[2] = (uint32_t)kMaxCtas + (uint32_t)draw % (uint32_t)kSlotPool;    // parking slots follow the accumulation slots
+                        misc[3] = (uint32_t)(old >> 16);            // runs that arrived before this one
+                    }
+                    named_bar_sync(1, C::EPI_THREADS);
+                    const bool last = misc[1] != 0;
+                    constexpr int V4 = CPT / 4;
+                    if (e == 0) FQ_TRACE(it - 1, 14);
+                    if (!last) {
+                        const uint32_t slot = misc[2];
+                        float4* sl = reinterpret_cast<float4*>(p.slots + (size_t)slot * kSlotFloats) + e;
+#pragma unroll
+                        for (int j = 0; j < V4; j++)
+                            __stcg(sl + j * C::EPI_THREADS, make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y));
+                        named_bar_sync(1, C::EPI_THREADS);          // every thread's stores are issued ...
+                        if (e == 0) {                               // ... and released, with the slot id, by one thread
+                            const int k = (int)misc[3];
+                            if (k >= kMaxParked) __trap();          // plan_ctas bounds the contributors of a tile
+                            *reinterpret_cast<volatile int*>(rec + 4 + k) = (int)slot;
+                            asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(rec + 1), "r"(ngr) : "memory");
+                        }
+                    } else {
+                        if (e == 0) {
+                            int parked, spins = 0;
+                            do {
+                                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(parked) : "l"(rec + 1) : "memory");
+                                if (++spins > (1 << 26)) __trap();
+                            } while (parked != G - ngr);
+                            const int np = (int)misc[3];             // everyone else arrived before the completing run
+                            for (int k = 0; k < np; k++) {
+                                misc[4 + k] = (uint32_t) * reinterpret_cast<volatile int*>(rec + 4 + k);
+                                rec[4 + k] = 0;
+                            }
+                            misc[3] = (uint32_t)np;
+                            rec[0] = 0; rec[1] = 0;                 // the record is this tile's alone: leave it zeroed
+                        }
+                        named_bar_sync(1, C::EPI_THREADS);
+                        if (e == 0) FQ_TRACE(it - 1, 15);
+                        const int npark = (int)misc[3];
+                        constexpr int CHK = V4 > 8 ? 8 : V4;        // 16-byte loads in flight per thread and parked tile
+                        for (int k = 0; k < npark; k++) {
+                            const float4* src = reinterpret_cast<const float4*>(p.slots + (size_t)misc[4 + k] * kSlotFloats) + e;
+#pragma unroll
+                            for (int j0 = 0; j0 < V4; j0 += CHK) {
+                                float4 v[CHK];
+#pragma unroll
+                                for (int j = 0; j < CHK; j++) v[j] = __ldcg(src + (j0 + j) * C::EPI_THREADS);
+#pragma unroll
+                                for (int j = 0; j < CHK; j++) {
+                                    acc[2 * (j0 + j)].x += v[j].x; acc[2 * (j0 + j)].y += v[j].y;
+                                    acc[2 * (j0 + j) + 1].x += v[j].z; acc[2 * (j0 + j) + 1].y += v[j].w;
                                 }
                             }
-                        };
-                        if (nl <= kMaxListed) {
-                            for (int i0 = 0; i0 < nl; i0 += KC) {
-                                float4 v[KC][V4];
-#pragma unroll
-                                for (int c = 0; c < KC; c++) {
-                                    if (i0 + c < nl) {
-                                        const float4* src = reinterpret_cast<const float4*>(p.slots + (size_t)misc[4 + i0 + c] * kSlotFloats) + e;
-#pragma unroll
-                                        for (int j = 0; j < V4; j++) v[c][j] = __ldcg(src + j * C::EPI_THREADS);
-                                    }
-                                }
-#pragma unroll
-                                for (int c = 0; c < KC; c++)
-                                    if (i0 + c < nl) add_run(v[c], i0 + c == 0);
-                            }
-                        } else {
-                            bool started = false;
-                            tile_contributors(p, mt, nt, [&](int sl_, int) {
-                                const float4* src = reinterpret_cast<const float4*>(p.slots + (size_t)sl_ * kSlotFloats) + e;
-                                float4 v[V4];
-#pragma unroll
-                                for (int j = 0; j < V4; j++) v[j] = __ldcg(src + j * C::EPI_THREADS);
-                                add_run(v, !started);
-                                started = true;
-                            });
                         }
 #pragma unroll
                         for (int j = 0; j < CPT; j++) {
@@ -926,9 +974,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             const float vsum = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
                             if (n2 < p.N && m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2, __half_as_ushort(__float2half_rn(vsum)));
                         }
-                        if (e == 0) p.cnt[first_slot] = 0;
                     }
-                    named_bar_sync(1, C::EPI_THREADS);              // flag word is reused by the next partial segment
+                    named_bar_sync(1, C::EPI_THREADS);              // the flag words are reused by the next cut run
+                    }
                 }
             }
             if (e == 0) FQ_TRACE(it - 1, 11);

@@ -56,7 +56,7 @@ size_t flexq_xscale_ref_halves(int M, int K);          /* K/128 * 2*ceil4(M)    
 size_t flexq_gemm_workspace_bytes(void);               /* split-K scratch, shape independent      */
 size_t flexq_linear_workspace_bytes(int M, int K);     /* gemm workspace + Xq + sx                */
 
-/* Zero a workspace once after allocation (the GEMM leaves its counters zeroed again after every call).
+/* Zero a workspace once after allocation (the GEMM leaves its cut-tile records zeroed again after every call).
  * One workspace must not be shared by GEMMs running concurrently on different streams. */
 int flexq_workspace_init(void* workspace, size_t bytes, void* stream);
 
@@ -120,12 +120,9 @@ int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, i
 
 /* Debug / tests (host only, no device work): the work decomposition of the GEMM.  For a problem of m_tiles token
  * tiles x n_tiles weight tiles x `groups` k-groups on at most max_ctas CTAs, writes the segments CTA `cta` walks as
- * int[5] = {token tile, n-tile, first group, end group, fp32 partial-sum slot or -1 when the run covers the whole tile} (up to
+ * int[5] = {token tile, n-tile, first group, end group, fp32 slot or -1 when the CTA covers the whole tile} (up to
  * `cap` of them), stores the number of CTAs launched in *n_ctas and returns the CTA's segment count.        */
 int flexq_debug_schedule(int m_tiles, int n_tiles, int groups, int max_ctas, int cta, int* segments, int cap, int* n_ctas);
-/* ... and the slots the CTA that completes tile (mt, nt) sums, in summation order (returns their number, 0 when every
- * CTA owns whole token tiles).                                                                                   */
-int flexq_debug_tile_contributors(int m_tiles, int n_tiles, int groups, int max_ctas, int mt, int nt, int* slots, int cap);
 
 /* Debug only: the GEMM with clock64 stamps of CTA 0's pipeline events, trace[unit][16]
  * (M <= 16 runs the decode tile, otherwise the 256-token tile); used by tools/trace.py. */
