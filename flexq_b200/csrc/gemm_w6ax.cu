@@ -377,6 +377,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if constexpr (M_TILE >= 128 && FLEXQ_PRODUCER_SLEEP_NS > 0) mbar_wait_sleepy<FLEXQ_PRODUCER_SLEEP_NS>(bar, parity);
         else mbar_wait_parked(bar, parity);
     };
+    constexpr int kEarlyW = C::NW < 3 ? C::NW : 3;
     // weight loads of steps [lo, hi) of this CTA (one thread)
     auto w_produce = [&](const int lo, const int hi) {
         // weights are read once when there is a single token tile (decode): keep them from
@@ -410,9 +411,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // The weight stream starts before the rest of the prologue (TMEM allocation, the other barriers, the CTA-wide
         // sync): weights are static, the ring is empty and its barriers are this thread's own -- at decode sizes the
         // prologue is ~0.5 us of a 6-12 us kernel.
+        // (three stages: each issue costs this thread ~300 cycles, and the CTA-wide sync below waits for it)
         for (int s = 0; s < C::NW; s++) { mbar_init(bar_w_full(s), 1); mbar_init(bar_w_empty(s), 128); }
         fence_barrier_init();
-        w_produce(0, C::NW);
+        w_produce(0, kEarlyW);
     }
     if (cw == 1) tmem_alloc<512>(smem_u32(&misc[0]));
     if constexpr (C::BIAS) {   // constant operand of the bias MMA, read through the async proxy
@@ -438,7 +440,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // ===================== TMA producer: packed weight tiles =====================
         reg_dealloc<32>();
         if (lane == 0) {
-            w_produce(C::NW, 0x7fffffff);
+            w_produce(kEarlyW, 0x7fffffff);
         } else if (TRACE && lane == 1 && blockIdx.x == (p.trace_units >> 16)) {
             // trace builds: an otherwise idle lane watches the "MMAs of step i retired" barriers (event 8)
             const int n = min(sch.b - sch.a, p.trace_units & 0xFFFF);
