@@ -69,13 +69,28 @@ struct GemmParams {
 #endif
 constexpr uint32_t kBiasB = 32u * 255u * 255u;
 
+// experiment switches of the epilogue (defaults = the measured best)
+#ifndef FLEXQ_EPI_WG
+#define FLEXQ_EPI_WG 3
+#endif
+#ifndef FLEXQ_EPI_FRAG
+#define FLEXQ_EPI_FRAG 1
+#endif
+#ifndef FLEXQ_EPI_TSTORE
+#define FLEXQ_EPI_TSTORE 1
+#endif
+
 template <int M_TILE, int GP>
 struct Cfg {
     static constexpr bool BIAS = (FLEXQ_BIASMMA != 0) && (M_TILE >= 128);
     // constant 0xFF operand region of the bias MMA: K-major, no swizzle, 8-row x 16-byte core matrices, two per
     // 8-row group (K = 32 bytes); shared by both operands (every byte is the same)
     static constexpr int ONES_BYTES = BIAS ? ((M_TILE > 128 ? M_TILE : 128) / 8) * 256 : 0;
-    static constexpr int SMEM_BUDGET = 222 * 1024 - ONES_BYTES;    // of the 227 KB a CTA may use
+    // fp16 staging tile of the output ([token][128 weight rows], two swizzle-128B boxes of 64 rows per epilogue
+    // warpgroup): the finished tile leaves through TMA stores instead of 2-byte scattered global stores
+    static constexpr bool TSTORE = (FLEXQ_EPI_TSTORE != 0) && (FLEXQ_EPI_FRAG != 0) && (FLEXQ_EPI_WG == 3) && BIAS && GP == 1;
+    static constexpr int STAGE_BYTES = TSTORE ? M_TILE * kTileN * 2 : 0;
+    static constexpr int SMEM_BUDGET = 222 * 1024 - ONES_BYTES - STAGE_BYTES;    // of the 227 KB a CTA may use
     // ---- TMEM columns: NAB accumulator step-buffers (GP groups x M_TILE) + NAT weight stages (GP x 32)
     static constexpr int ACC_COLS = GP * M_TILE;
     static constexpr int A_COLS = GP * 32;
@@ -105,7 +120,8 @@ struct Cfg {
     // number of stages so that each stage is always consumed by the same issuer: an mbarrier parity
     // wait cannot tell phase p from phase p+2, so an issuer must never skip a phase of a barrier.
     static_assert(NX % 2 == 0 && NAT % 2 == 0 && NAB % 2 == 0, "issuer-consumed rings need even depth");
-    static constexpr int OFF_X = 0;
+    static constexpr int OFF_STAGE = 0;
+    static constexpr int OFF_X = STAGE_BYTES;
     static constexpr int OFF_W = OFF_X + NX * X_BYTES;
     static constexpr int OFF_S = OFF_W + NW * W_BYTES;
     static constexpr int OFF_BAR = OFF_S + NS * S_BYTES;
@@ -118,9 +134,6 @@ struct Cfg {
     // beat 2 x 96 columns (8 warps, 200 regs) by 3-8 % on the 192-token tile -- one more warp per scheduler to
     // cover FFMA2 dependencies; 4 x 48 columns are 4 % slower again (per-warp step overhead).  The 128-token
     // tile and the decode tiles keep 2.
-#ifndef FLEXQ_EPI_WG
-#define FLEXQ_EPI_WG 3
-#endif
     static constexpr int EPI_WG = (FLEXQ_EPI_WG == 4 && M_TILE >= 128) ? 4 : (FLEXQ_EPI_WG == 3 && M_TILE == 192) ? 3 : 2;
     static constexpr int EPI_THREADS = 128 * EPI_WG;
     static constexpr int THREADS = 256 + EPI_THREADS;
@@ -148,9 +161,6 @@ struct Cfg {
     // of every 4 accumulator elements, how many get their float bias by LOP3 (ALU pipe) instead of an
     // integer add (FMA pipe): balances the two pipes against the expander's ALU work (measured per tile)
     static constexpr int MAGIC_LOPS = (M_TILE >= 192) ? FLEXQ_LOPS_BIG : FLEXQ_LOPS_SMALL;
-#ifndef FLEXQ_EPI_FRAG
-#define FLEXQ_EPI_FRAG 1
-#endif
     // Fragment layout of the TMEM drain (tcgen05.ld.16x256b): a thread holds 4 rows x 16 columns of its warpgroup's
     // 128 x 64 slice instead of 1 row x 64 columns, so it needs 16 token scales per k-group instead of 64 (8 LDS.64
     // touching 32 contiguous bytes per warp instead of 16 broadcast LDS.128) -- the shared-memory data pipe, which
@@ -320,7 +330,8 @@ __device__ __forceinline__ float magic_f32(uint32_t s) {
 template <int M_TILE, int GP, bool DUMP, bool TRACE>
 __global__ void __launch_bounds__(Cfg<M_TILE, GP>::THREADS, 1)
 w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_sx,
-                 const __grid_constant__ CUtensorMap tmap_sw, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_sw, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_d, const GemmParams p) {
     using C = Cfg<M_TILE, GP>;
     // how tiles cut by a range boundary are summed (see the epilogue): parked partial tiles for the 192-token tile
     // (contributors arrive far apart: measured 2-11 % faster at M >= 512), shared-slot reductions for the smaller
@@ -645,6 +656,64 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         constexpr bool PREFETCH = (FLEXQ_EPI_PREFETCH != 0) && GP == 1 && ((CPT / CH) % 2 == 0) && !kRearm;
         bool pre = false;
         const int n_steps = sch.b - sch.a;
+        // Finished tile -> D.  Fragment layout with staging (TSTORE): lanes l and l ^ 4 hold neighbouring weight rows of the
+        // same two tokens; one exchange gives each a (row, row + 1) pair of one token, packed to a half2 and stored to the
+        // warpgroup's staging tile ([token][64 rows] boxes, swizzle-128B: the 8 token rows a warp touches land in 8
+        // different 16-byte columns, conflict free); one thread per warpgroup then issues two TMA stores (rows / tokens
+        // beyond N / M are clipped by the tensor map).  2-byte global stores straight from the fragment cost the LSU a
+        // sector per 16 bytes (measured: 8 % of the epilogue's stall samples at K = 8192, proportionally more at smaller K).
+        const bool odd_row = (lane >> 2) & 1;
+        const uint32_t stage0 = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u + (uint32_t)(quad >> 1) * 8192u +
+                                (uint32_t)(fc0 + (odd_row ? 1 : 0)) * 128u + 2u * (uint32_t)((lane >> 2) & ~1);
+        const uint32_t stage_x = (uint32_t)(4 * (quad & 1)) ^ (uint32_t)(fc0 + (odd_row ? 1 : 0));   // 16-byte column before the k term
+        auto store_tile = [&](const int mt, const int nt, const int n, const bool n_ok, const int mbase) {
+            if constexpr (C::TSTORE && !DUMP) {
+                if ((e & 127) == 0) bulk_wait_read_all();            // the previous tile's stores have read the staging tile
+                named_bar_sync(2 + wg_id, 128);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t ak = stage0 + (((stage_x ^ (uint32_t)k) & 7u) << 4);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float2 a = acc[k * 8 + i];
+                        const float keep = odd_row ? a.y : a.x, send = odd_row ? a.x : a.y;
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                        const __half2 h = __floats2half2_rn(kOutScale * (odd_row ? recv : keep), kOutScale * (odd_row ? keep : recv));
+                        sts_u32(ak + (uint32_t)i * 1024u, *reinterpret_cast<const uint32_t*>(&h));
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2 + wg_id, 128);
+                if ((e & 127) == 0) {
+                    const uint32_t st = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u;
+                    tma_store_2d(&tmap_d, st, nt * kTileN, mt * M_TILE + col0);
+                    if (nt * kTileN + 64 < p.N) tma_store_2d(&tmap_d, st + 8192u, nt * kTileN + 64, mt * M_TILE + col0);
+                    bulk_commit_group();
+                }
+            } else if constexpr (C::FRAG) {
+                // acc[k * 8 + j].{x,y}: row fr0 + 8k, column col0 + 8j + fc0 + {0,1}
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int n2 = nt * kTileN + fr0 + 8 * k;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int m = mbase + 8 * j + fc0;
+                        unsigned short* dst = reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2;
+                        if (n2 < p.N && m < p.M) __stcs(dst, __half_as_ushort(__float2half_rn(kOutScale * acc[k * 8 + j].x)));
+                        if (n2 < p.N && m + 1 < p.M) __stcs(dst + p.N, __half_as_ushort(__float2half_rn(kOutScale * acc[k * 8 + j].y)));
+                    }
+                }
+            } else {
+                if (n_ok) {
+#pragma unroll
+                    for (int j = 0; j < CPT; j++) {
+                        const int m = mbase + j;
+                        const float a = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
+                        if (m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n, __half_as_ushort(__float2half_rn(a)));   // streaming: do not displace X/W in L2
+                    }
+                }
+            }
+        };
         walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             const int n = nt * kTileN + r;
             const int mbase = mt * M_TILE + col0;
@@ -830,29 +899,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             if (e == 0) FQ_TRACE(it - 1, 10);
             if constexpr (!DUMP) {
-                if (C::FRAG && g0 == 0 && g1 == G) {
-                    // acc[k * 8 + j].{x,y}: row fr0 + 8k, column col0 + 8j + fc0 + {0,1}
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int n2 = nt * kTileN + fr0 + 8 * k;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int m = mbase + 8 * j + fc0;
-                            unsigned short* dst = reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2;
-                            if (n2 < p.N && m < p.M) __stcs(dst, __half_as_ushort(__float2half_rn(kOutScale * acc[k * 8 + j].x)));
-                            if (n2 < p.N && m + 1 < p.M) __stcs(dst + p.N, __half_as_ushort(__float2half_rn(kOutScale * acc[k * 8 + j].y)));
-                        }
-                    }
-                } else if (g0 == 0 && g1 == G) {
-                    // whole tile reduced by this CTA: store fp16 directly
-                    if (n_ok) {
-#pragma unroll
-                        for (int j = 0; j < CPT; j++) {
-                            const int m = mbase + j;
-                            const float a = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
-                            if (m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n, __half_as_ushort(__float2half_rn(a)));   // streaming: do not displace X/W in L2
-                        }
-                    }
+                if (g0 == 0 && g1 == G) {
+                    store_tile(mt, nt, n, n_ok, mbase);      // whole tile reduced by this CTA
                 } else {
                     if constexpr (!kHandoff) {
                     // Tile cut by a range boundary, reduction variant: every contributor adds its fp32 partial tile into
@@ -887,13 +935,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         if (TRACE && e == 0 && acc[0].x != 12345.f) FQ_TRACE(it - 1, 15);      // depends on the first load
 #pragma unroll
                         for (int j = 0; j < CPT / 4; j++) __stcg(sl + j * C::EPI_THREADS, make_float4(0.f, 0.f, 0.f, 0.f));
-#pragma unroll
-                        for (int j = 0; j < CPT; j++) {
-                            const int m = C::FRAG ? mbase + 8 * ((j >> 1) & 7) + fc0 + (j & 1) : mbase + j;
-                            const int n2 = C::FRAG ? nt * kTileN + fr0 + 8 * (j >> 4) : n;
-                            const float vsum = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
-                            if (n2 < p.N && m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2, __half_as_ushort(__float2half_rn(vsum)));
-                        }
+                        store_tile(mt, nt, n, n_ok, mbase);
                         if (e == 0) rec[0] = 0;
                     }
                     named_bar_sync(1, C::EPI_THREADS);              // flag word is reused by the next partial segment
@@ -969,13 +1011,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                 }
                             }
                         }
-#pragma unroll
-                        for (int j = 0; j < CPT; j++) {
-                            const int m = C::FRAG ? mbase + 8 * ((j >> 1) & 7) + fc0 + (j & 1) : mbase + j;
-                            const int n2 = C::FRAG ? nt * kTileN + fr0 + 8 * (j >> 4) : n;
-                            const float vsum = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
-                            if (n2 < p.N && m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2, __half_as_ushort(__float2half_rn(vsum)));
-                        }
+                        store_tile(mt, nt, n, n_ok, mbase);
                     }
                     named_bar_sync(1, C::EPI_THREADS);              // the flag words are reused by the next cut run
                     }
@@ -985,6 +1021,11 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     });
     }
 
+    if constexpr (C::TSTORE && !DUMP) {      // the last tile's TMA stores must have left shared memory before the CTA exits
+        if (warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG && ((threadIdx.x - 32 * C::EPI_WARP0) & 127) == 0) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) FQ_TRACE(0, 12);
@@ -1116,6 +1157,15 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
         tmap_sw = tmap_x;
     }
 
+    CUtensorMap tmap_d = tmap_x;
+    if (C::TSTORE && !DUMP) {   // D [M][N] fp16 seen as boxes of 64 weight rows (128 bytes, swizzle-128B) x 64 tokens
+        const cuuint64_t dims_d[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
+        const cuuint64_t str_d[1] = {(cuuint64_t)p.N * 2};
+        const cuuint32_t box_d[2] = {64u, 64u};
+        if (enc(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.D, dims_d, str_d, box_d, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return FLEXQ_ERR_TENSORMAP;
+    }
     p.n_tiles = ceil_div(p.N, kTileN);
     p.m_tiles = ceil_div(p.M, M_TILE);
     {
@@ -1142,7 +1192,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, tmap_x, tmap_sx, tmap_sw, tmap_w, p);
+    return (int)cudaLaunchKernelEx(&cfg, w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, tmap_x, tmap_sx, tmap_sw, tmap_w, tmap_d, p);
 }
 
 template <bool DUMP>
