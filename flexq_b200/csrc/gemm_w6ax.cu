@@ -259,11 +259,17 @@ __host__ __device__ __forceinline__ int tile_slot(const GemmParams& p, int mt, i
 }
 
 // host: fill the decomposition fields of p (n_tiles, m_tiles, G set) for at most max_ctas CTAs
-static void plan_ctas(GemmParams& p, int max_ctas) {
+// what summing a cut tile costs a CTA, in steps of that tile configuration (measured from pipeline traces)
+template <int M_TILE> constexpr int kFixSteps = M_TILE >= 128 ? 16 : M_TILE >= 64 ? 6 : M_TILE >= 32 ? 4 : 3;
+
+// Returns the plan's estimated length in steps (gp = k-groups per step of the tile configuration; fix_steps = what summing
+// a cut tile costs, in steps: the tail of the kernel that nothing overlaps).
+static int plan_ctas(GemmParams& p, int max_ctas, int gp = 1, int fix_steps = 0) {
     const long long Umt = (long long)p.n_tiles * p.G;
+    auto steps_of = [&](long long groups) { return (int)((groups + gp - 1) / gp); };
     if (p.m_tiles > max_ctas) {
         p.whole_rows = 1; p.P = max_ctas; p.R = max_ctas; p.Pn = 1; p.Ureg = (int)Umt;
-        return;
+        return ceil_div(p.m_tiles, p.P) * p.n_tiles * steps_of(p.G);
     }
     p.whole_rows = 0;
     p.R = p.m_tiles;
@@ -275,25 +281,32 @@ static void plan_ctas(GemmParams& p, int max_ctas) {
     if (p.Pn > Umt / min_units) {
         p.Pn = (int)(Umt / min_units) > 0 ? (int)(Umt / min_units) : 1;
         p.P = p.R * p.Pn; p.Ureg = (int)Umt;
-        return;
+        return steps_of(ceil_div((int)Umt, p.Pn)) + fix_steps;
     }
-    // Small problems (fewer n-tiles than columns): when a whole number C of columns per n-tile keeps >= 80 % of the
-    // CTAs busy, cut every tile into exactly C runs.  Every CTA then walks one run of one tile -- one partial-tile
-    // fix-up per CTA instead of two (a range that straddles a tile boundary ends one tile and starts another), and the
-    // fix-up is the serial tail of a kernel that is only a few microseconds long.
-    static const int align_pct = [] { const char* e = getenv("FLEXQ_ALIGN_PCT"); return e ? atoi(e) : 80; }();
-    if (p.Pn >= p.n_tiles && p.Pn < Umt) {
-        const int aligned = p.Pn / p.n_tiles * p.n_tiles;
-        if ((long long)aligned * p.R * 100 >= (long long)max_ctas * align_pct) {
+    // stream-K over all CTAs: the regular columns plus the spare CTAs that do not fill another column
+    int spare = p.Pn < Umt ? max_ctas - p.R * p.Pn : 0;
+    int P_sk = p.R * p.Pn + spare;
+    int Ureg = spare ? (int)((Umt * p.R * p.Pn + P_sk / 2) / P_sk) : (int)Umt;
+    // every regular CTA and every spare CTA must own at least one unit
+    if (spare && (Ureg < p.Pn || (long long)p.R * (Umt - Ureg) < spare)) { P_sk = p.R * p.Pn; Ureg = (int)Umt; }
+    const bool sk_cuts = (Umt * p.R) % P_sk != 0 || (Umt * p.R / P_sk) % p.G != 0;
+    const int cost_sk = steps_of((Umt * p.R + P_sk - 1) / P_sk) + (sk_cuts ? fix_steps : 0);
+    // Fewer n-tiles than columns: a whole number C of columns per n-tile cuts every tile into exactly C runs, so every
+    // CTA walks one run of one tile -- one cut-tile sum per CTA (none when C = 1) instead of two (a range that straddles
+    // a tile boundary ends one tile and starts another).  Taken when its estimated length, with fewer CTAs at work, is
+    // not longer; memory-bound decode tiles (gp > 1) additionally keep >= 70 % of the SMs streaming.
+    static const bool allow_aligned = [] { const char* e = getenv("FLEXQ_ALIGN"); return !(e && e[0] == '0'); }();
+    if (allow_aligned && p.Pn >= p.n_tiles && p.Pn < Umt) {
+        const int aligned = p.Pn / p.n_tiles * p.n_tiles, C = aligned / p.n_tiles;
+        const int cost_al = steps_of(ceil_div(p.G, C)) + (C > 1 ? (fix_steps + 1) / 2 : 0);
+        const bool enough_sms = gp == 1 || (long long)aligned * p.R * 100 >= (long long)max_ctas * 70;
+        if (cost_al <= cost_sk && enough_sms) {
             p.Pn = aligned; p.P = p.R * p.Pn; p.Ureg = (int)Umt;
-            return;
+            return cost_al;
         }
     }
-    int spare = p.Pn < Umt ? max_ctas - p.R * p.Pn : 0;
-    p.P = p.R * p.Pn + spare;
-    p.Ureg = spare ? (int)((Umt * p.R * p.Pn + p.P / 2) / p.P) : (int)Umt;
-    // every regular CTA and every spare CTA must own at least one unit
-    if (spare && (p.Ureg < p.Pn || (long long)p.R * (Umt - p.Ureg) < spare)) { p.P = p.R * p.Pn; p.Ureg = (int)Umt; }
+    p.P = P_sk; p.Ureg = Ureg;
+    return cost_sk;
 }
 
 // debug / test: the segments (mt, nt, g0, g1, slot) CTA `cta` walks for a problem of m_tiles x n_tiles x G units on at
@@ -301,7 +314,7 @@ static void plan_ctas(GemmParams& p, int max_ctas) {
 int debug_schedule(int m_tiles, int n_tiles, int G, int max_ctas, int cta, int* out, int cap, int* n_ctas) {
     GemmParams p{};
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.G = G;
-    plan_ctas(p, max_ctas);
+    plan_ctas(p, max_ctas, 1, kFixSteps<192>);          // the plan of the prefill tiles (1 group per step)
     if (n_ctas) *n_ctas = p.P;
     if (cta < 0 || cta >= p.P) return 0;
     int n = 0;
@@ -1171,7 +1184,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     {
         int max_ctas = sms < kMaxCtas ? sms : kMaxCtas;
         if (g_sm_limit > 0 && g_sm_limit < max_ctas) max_ctas = g_sm_limit;
-        plan_ctas(p, max_ctas);
+        plan_ctas(p, max_ctas, GP, kFixSteps<M_TILE>);
     }
     const int P = p.P;
 
@@ -1202,12 +1215,24 @@ static int dispatch(const GemmArgs& a, cudaStream_t stream) {
     if (M <= 32) return launch<32, 4, DUMP>(a, stream);
     if (M <= 64) return launch<64, 2, DUMP>(a, stream);
     if (M <= 128) return launch<128, 1, DUMP>(a, stream);
-    // token tile for large M: 192 (fewer weight expansions per MMA) unless 128 wastes fewer padded rows
+    // Token tile for large M, by estimated length of the two plans: a 192-token step runs 1.2 x as long as a 128-token
+    // step (measured, equal padded rows: 192 is 20-30 % faster per row), summing a cut tile costs ~16 steps either way.
     static int force = -1;
     if (force < 0) { const char* e = getenv("FLEXQ_MTILE"); force = e ? atoi(e) : 0; }
-    // rows actually computed with each tile; the 192-token tile runs ~15% faster per row (measured, 70B shapes)
-    const int rows192 = ceil_div(M, 192) * 192, rows128 = ceil_div(M, 128) * 128;
-    const bool use128 = force ? force == 128 : (rows128 * 100 < rows192 * 85);
+    bool use128;
+    if (force) use128 = force == 128;
+    else {
+        const int sms = num_sms();
+        int max_ctas = sms < kMaxCtas ? sms : kMaxCtas;
+        if (g_sm_limit > 0 && g_sm_limit < max_ctas) max_ctas = g_sm_limit;
+        GemmParams q = a.p;
+        q.n_tiles = ceil_div(q.N, kTileN);
+        q.m_tiles = ceil_div(M, 192);
+        const int len192 = plan_ctas(q, max_ctas, 1, kFixSteps<192>);
+        q.m_tiles = ceil_div(M, 128);
+        const int len128 = plan_ctas(q, max_ctas, 1, kFixSteps<128>);
+        use128 = len128 * 5 < len192 * 6;
+    }
     if (use128) return launch<128, 1, DUMP>(a, stream);
     return launch<192, 1, DUMP>(a, stream);
 }
