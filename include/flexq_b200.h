@@ -124,8 +124,9 @@ int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, i
  * `cap` of them), stores the number of CTAs launched in *n_ctas and returns the CTA's segment count.        */
 int flexq_debug_schedule(int m_tiles, int n_tiles, int groups, int max_ctas, int cta, int* segments, int cap, int* n_ctas);
 
-/* Debug only: the GEMM with clock64 stamps of CTA 0's pipeline events, trace[unit][16]
- * (M <= 16 runs the decode tile, otherwise the 256-token tile); used by tools/trace.py. */
+/* Debug only: the GEMM with clock64 stamps of one CTA's pipeline events, trace[unit][16],
+ * plus per-CTA wall-clock windows (token tile by M as in flexq_gemm_w6ax: 16 / 32 / 64 / 128, above that always
+ * the 192-token tile); trace_units = steps to stamp | traced CTA << 16; used by tools/trace.py. */
 int flexq_debug_gemm_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale_half,
                            void* d_half, int M, int N, int K, void* workspace, long long* trace,
                            int trace_units, void* stream);

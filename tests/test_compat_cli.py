@@ -64,3 +64,26 @@ def test_cublas_cli():
 def test_ft_wrapper(m, xb):
     r = _run("test_ft_wrapper", m, 4096, 4096, xb)
     assert r.returncode == 0 and "FT wrapper SUCCESS" in r.stdout, r.stdout + r.stderr
+
+
+def test_sweep_scripts_enumerate_the_reference_shapes(tmp_path):
+    """compat/test_flexq_kernel.sh / test_cublas_kernel.sh (role of the reference's engine/test_*_kernel.sh): with the
+    harness binaries replaced by stubs, they must produce one result file per (model, batch, layer) with the reference's
+    file names and argv (M N K X_BITS W_BITS); needs no GPU."""
+    import shutil
+    work = tmp_path / "compat"
+    (work / "bin").mkdir(parents=True)
+    for s in ("test_flexq_kernel.sh", "test_cublas_kernel.sh"):
+        shutil.copy(os.path.join(ROOT, "compat", s), work / s)
+    for exe in ("test_bgemm_kernel", "test_cublas_kernel"):
+        p = work / "bin" / exe
+        p.write_text("#!/bin/sh\necho \"$@\"\n")
+        p.chmod(0o755)
+    env = dict(os.environ, BS="1 8")
+    for s in ("test_flexq_kernel.sh", "test_cublas_kernel.sh"):
+        subprocess.run(["bash", str(work / s)], check=True, env=env, timeout=120)
+    got = sorted(os.listdir(work / "flexq_results"))
+    assert len(got) == 2 * 5 * 4 and got == sorted(os.listdir(work / "cublas_results"))
+    assert "llama_2_70b_8x8192x28672_w6a8.txt" in got and "llama_7b_1x12288x4096_w6a6.txt" in got and "opt_30b_1x21504x7168_w6a6.txt" in got
+    assert (work / "flexq_results" / "llama_2_70b_8x8192x28672_w6a8.txt").read_text().split() == ["8", "8192", "28672", "8", "6"]
+    assert (work / "cublas_results" / "llama_2_13b_1x13824x5120_w6a6.txt").read_text().split() == ["1", "13824", "5120"]
