@@ -89,10 +89,23 @@ __device__ __forceinline__ void multimem_st_f16x8(void* mc, const uint4& v) {
                  : "memory");
 }
 
+// 16-byte vectors a thread of the multicast kernel keeps in flight (all loads of an iteration are issued before the first
+// store); FLEXQ_AR_UNROLL (1, 2, 4, 8) overrides it at run time.  Measured on 8 x B200 (tools/ar_probe.py,
+// profiles/ar_probe_tp8_r2.txt): the time does not depend on it, nor on the number of blocks beyond 8 -- 22 us fixed
+// (two symmetric-memory barriers) + 2.2 us per MB, i.e. the in-switch reduction runs at ~460 GB/s whatever is in flight,
+// and a free-running grid is slower (119 us for 32 MB) than 8 blocks of 1024 threads (92 us).
 #ifndef FLEXQ_AR_UNROLL
 #define FLEXQ_AR_UNROLL 4
 #endif
-constexpr int kArUnroll = FLEXQ_AR_UNROLL;
+static int ar_unroll() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("FLEXQ_AR_UNROLL");
+        const int n = e ? atoi(e) : FLEXQ_AR_UNROLL;
+        v = (n == 1 || n == 2 || n == 4 || n == 8) ? n : FLEXQ_AR_UNROLL;
+    }
+    return v;
+}
 // 0: free-running grid (up to 4 x 148 blocks of 256 threads).  n > 0: at most n blocks of 1024 threads -- used while a
 // persistent GEMM (one CTA per SM, all of its shared memory) runs on the other SMs: every SM that hosts even one small
 // block of ours is lost to the GEMM, so the reduction is packed onto as few SMs as the GEMM leaves free.
@@ -100,6 +113,7 @@ static int g_ar_blocks = 0;
 void set_allreduce_blocks(int n) { g_ar_blocks = n > 0 ? n : 0; }
 
 // vec0 .. vec1: this rank's range of 16-byte vectors
+template <int UNROLL>
 __global__ void __launch_bounds__(1024) allreduce_multimem_kernel(__half* mc, long long vec0, long long vec1, FlagPtrs flags, int rank,
                                                                  int world) {
     const bool synced = flags.p[0] != nullptr;
@@ -108,12 +122,12 @@ __global__ void __launch_bounds__(1024) allreduce_multimem_kernel(__half* mc, lo
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = vec0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint4* base = reinterpret_cast<uint4*>(mc);
-    for (; i + (kArUnroll - 1) * stride < vec1; i += kArUnroll * stride) {
-        uint4 v[kArUnroll];
+    for (; i + (UNROLL - 1) * stride < vec1; i += UNROLL * stride) {
+        uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < kArUnroll; u++) v[u] = multimem_ld_reduce_f16x8(base + i + u * stride);
+        for (int u = 0; u < UNROLL; u++) v[u] = multimem_ld_reduce_f16x8(base + i + u * stride);
 #pragma unroll
-        for (int u = 0; u < kArUnroll; u++) multimem_st_f16x8(base + i + u * stride, v[u]);
+        for (int u = 0; u < UNROLL; u++) multimem_st_f16x8(base + i + u * stride, v[u]);
     }
     for (; i < vec1; i += stride) multimem_st_f16x8(base + i, multimem_ld_reduce_f16x8(base + i));
     if (synced) ar_close(flags, rank, world, epoch);
@@ -261,10 +275,17 @@ int allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, void* const* 
     const long long work = vec1 > vec0 ? vec1 - vec0 : 0;
     const int threads = g_ar_blocks > 0 ? 1024 : 256;
     const long long cap = g_ar_blocks > 0 ? g_ar_blocks : 4 * 148;
-    long long nb = (work + threads * kArUnroll - 1) / (threads * kArUnroll);
+    const int unroll = multicast_ptr ? ar_unroll() : 4;
+    long long nb = (work + threads * unroll - 1) / (threads * unroll);
     const int blocks = (int)(nb > cap ? cap : (nb < 1 ? 1 : nb));
     if (multicast_ptr) {
-        allreduce_multimem_kernel<<<blocks, threads, 0, stream>>>(reinterpret_cast<__half*>(multicast_ptr), vec0, vec1, fp, rank, world);
+        __half* mc = reinterpret_cast<__half*>(multicast_ptr);
+        switch (unroll) {
+            case 1: allreduce_multimem_kernel<1><<<blocks, threads, 0, stream>>>(mc, vec0, vec1, fp, rank, world); break;
+            case 2: allreduce_multimem_kernel<2><<<blocks, threads, 0, stream>>>(mc, vec0, vec1, fp, rank, world); break;
+            case 4: allreduce_multimem_kernel<4><<<blocks, threads, 0, stream>>>(mc, vec0, vec1, fp, rank, world); break;
+            default: allreduce_multimem_kernel<8><<<blocks, threads, 0, stream>>>(mc, vec0, vec1, fp, rank, world); break;
+        }
         return (int)cudaGetLastError();
     }
     PeerPtrs pp{};

@@ -46,6 +46,8 @@ struct GemmParams {
     int P, Pn, R;            // P CTAs: R rows x Pn columns of regular CTAs + (P - R*Pn) spare ones (see Sched)
     int Ureg;                // units [0, Ureg) of every token tile belong to the regular CTAs
     int whole_rows;          // 1: more token tiles than CTAs, every CTA owns whole token tiles
+    int cluster;             // > 1: launched as thread-block clusters of this many CTAs, the runs of one weight tile; its
+                             // partial sums meet in the first CTA's shared memory (decode tiles, aligned plan)
     long long* trace;        // TRACE builds: [step][16] clock64 stamps of CTA 0
     int trace_units;
 };
@@ -79,6 +81,11 @@ constexpr uint32_t kBiasB = 32u * 255u * 255u;
 #ifndef FLEXQ_EPI_TSTORE
 #define FLEXQ_EPI_TSTORE 1
 #endif
+#ifndef FLEXQ_CLUSTER
+#define FLEXQ_CLUSTER 1
+#endif
+
+constexpr int kClusterMaxTile = 16;      // largest token tile that sums cut tiles through a thread-block cluster
 
 template <int M_TILE, int GP>
 struct Cfg {
@@ -350,6 +357,14 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // (contributors arrive far apart: measured 2-11 % faster at M >= 512), shared-slot reductions for the smaller
     // tiles, whose contributors finish together (hand-off 5-65 % slower there: the completing CTA waits for the rest)
     constexpr bool kHandoff = (FLEXQ_FIXUP_HANDOFF != 0) && M_TILE == 192;
+    // Decode tiles under the aligned plan run as clusters: the C runs of a weight tile are C consecutive CTAs, which finish
+    // together; instead of meeting in global memory (reductions, a fence, an atomic and a load back: 2400-3800 cycles
+    // of a 6-12 us kernel) the partial tiles are written into the first CTA's shared memory (the weight ring, idle by
+    // then) between two cluster barriers and summed there in rank order.
+    // Measured (profiles/r2_experiments/sweep_b20_*): 1.5-4.5 % at M <= 16 (most of what looks like cut-tile cost in a trace
+    // is skew between the contributors, which no protocol removes); the 32- and 64-token tiles move 16-32 KB per CTA through
+    // distributed shared memory and come out 3-9 % slower, so they keep the reductions.
+    constexpr bool kClusterOk = (FLEXQ_CLUSTER != 0) && M_TILE <= kClusterMaxTile && !DUMP;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -727,6 +742,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
         };
+        int c_mt = 0, c_nt = 0;
         walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             const int n = nt * kTileN + r;
             const int mbase = mt * M_TILE + col0;
@@ -914,6 +930,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if constexpr (!DUMP) {
                 if (g0 == 0 && g1 == G) {
                     store_tile(mt, nt, n, n_ok, mbase);      // whole tile reduced by this CTA
+                } else if (kClusterOk && p.cluster > 1) {
+                    // the CTA's only run (aligned plan): its partial sums stay in registers for the cluster exchange below
+                    c_mt = mt; c_nt = nt;
                 } else {
                     if constexpr (!kHandoff) {
                     // Tile cut by a range boundary, reduction variant: every contributor adds its fp32 partial tile into
@@ -1032,8 +1051,38 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
             if (e == 0) FQ_TRACE(it - 1, 11);
                     });
+        if (kClusterOk && p.cluster > 1) {
+            const uint32_t crank = blockIdx.x % (uint32_t)p.cluster;
+            constexpr int V4 = CPT / 4;
+            constexpr uint32_t kPart = M_TILE * kTileN * 4;          // bytes of one partial tile, thread-linear [quad][thread]
+            const uint32_t mine = smem_base + C::OFF_W + (uint32_t)e * 16u;
+            cluster_sync_all();                                      // every CTA of the cluster has drained its weight ring
+            if (crank != 0) {
+                const uint32_t dst = cluster_map_shared(mine + (crank - 1) * kPart, 0);
+#pragma unroll
+                for (int j = 0; j < V4; j++)
+                    st_cluster_f4(dst + (uint32_t)j * C::EPI_THREADS * 16u, make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y));
+            }
+            cluster_sync_all();                                      // the partial tiles have landed in rank 0
+            if (crank == 0) {
+                for (uint32_t rk = 1; rk < (uint32_t)p.cluster; rk++) {      // rank order: the same bits every run
+#pragma unroll
+                    for (int j = 0; j < V4; j++) {
+                        const float4 v = lds_f4(mine + (rk - 1) * kPart + (uint32_t)j * C::EPI_THREADS * 16u);
+                        acc[2 * j].x += v.x; acc[2 * j].y += v.y; acc[2 * j + 1].x += v.z; acc[2 * j + 1].y += v.w;
+                    }
+                }
+                const int n = c_nt * kTileN + r;
+                store_tile(c_mt, c_nt, n, n < p.N, c_mt * M_TILE + col0);
+            }
+            if (e == 0) FQ_TRACE(it - 1, 11);
+        }
     }
 
+    if (kClusterOk && p.cluster > 1 && !(warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG)) {
+        cluster_sync_all();      // the two barriers of the epilogue's cluster exchange: every thread of the cluster takes part
+        cluster_sync_all();
+    }
     if constexpr (C::TSTORE && !DUMP) {      // the last tile's TMA stores must have left shared memory before the CTA exits
         if (warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG && ((threadIdx.x - 32 * C::EPI_WARP0) & 127) == 0) {
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1107,6 +1156,16 @@ static bool pdl_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("FLEXQ_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// FLEXQ_CLUSTER_RUNTIME=0 disables the cluster launch of decode tiles (A/B experiments)
+static bool cluster_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FLEXQ_CLUSTER_RUNTIME");
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
@@ -1200,11 +1259,39 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    // Decode tiles, aligned plan with C runs per weight tile: launch the C CTAs of a tile as one cluster (see kClusterOk in
+    // the kernel) when C partial tiles fit the weight ring of the first CTA and the device can hold all clusters at once
+    p.cluster = 0;
+    if (FLEXQ_CLUSTER && !DUMP && M_TILE <= kClusterMaxTile && !p.whole_rows && p.m_tiles == 1 && p.P == p.Pn && p.Pn % p.n_tiles == 0 && cluster_enabled()) {
+        const int Cn = p.Pn / p.n_tiles;
+        constexpr int kFit = 1 + (C::NW * C::W_BYTES) / (M_TILE * kTileN * 4);
+        if (Cn >= 2 && Cn <= 8 && Cn <= kFit) {
+            static std::atomic<int> resident[kMaxDevices][9];         // 1 + clusters of this size the device holds at once (0 = unknown)
+            int f = resident[dev][Cn].load(std::memory_order_acquire);
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = Cn; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+            cfg.numAttrs = na + 1;
+            if (f == 0) {
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, &cfg) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    nclusters = 0;
+                }
+                f = 1 + nclusters;
+                resident[dev][Cn].store(f, std::memory_order_release);
+            }
+            if (f - 1 >= p.P / Cn) { p.cluster = Cn; na++; }       // a second wave of clusters would double the kernel
+        }
+    }
+    cfg.numAttrs = na;
     return (int)cudaLaunchKernelEx(&cfg, w6ax_gemm_kernel<M_TILE, GP, DUMP, TRACE>, tmap_x, tmap_sx, tmap_sw, tmap_w, tmap_d, p);
 }
 

@@ -591,6 +591,34 @@ def test_gemm_every_decomposition_vs_exact(capi, M, N, K, xb):
         assert ((o.float() - outs[0].float()).abs() <= 2e-3 * outs[0].float().abs() + 1e-6).all()
 
 
+@pytest.mark.parametrize("M,N,K,xb,exact", [(16, 4096, 4096, 6, True), (1, 6144, 4096, 6, False), (32, 4096, 14336, 8, False),
+                                             (64, 8192, 8192, 6, False), (9, 4096, 11008 // 128 * 128, 8, True), (16, 8192, 8192, 6, True),
+                                             (7, 2560, 4096, 6, False)])
+def test_gemm_decode_cluster_exchange(capi, M, N, K, xb, exact):
+    """Decode problems whose plan cuts every weight tile into C runs (C = 4, 3, 4, 2, 4, 2, 7 here).  With the 16-token
+    tile and a cluster size the device can hold in one wave (`exact` cases) the C CTAs run as a thread-block cluster: the
+    partial tiles meet in the first CTA's shared memory and are summed in rank order -- bit-identical from launch to launch
+    (no atomics on data).  The other cases take the reduction path and agree to one fp16 rounding."""
+    dev = torch.device("cuda")
+    torch.manual_seed(3 * M + N + K)
+    w6, wsc = capi.quant_pack_w6((0.02 * torch.randn(N, K, device=dev)).half())
+    x = torch.randn(M, K, device=dev).half()
+    xq, sx = capi.quant_act(x, xb)
+    ws = capi.new_workspace()
+    ref = _exact_w6ax(capi, xq, sx, w6, wsc, N)
+    outs = [capi.gemm_w6ax(xq, sx, w6, wsc, N, ws).clone() for _ in range(6)]
+    torch.cuda.synchronize()
+    err = (outs[0].double() - ref).abs()
+    assert (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item() <= RMS_REL_TOL
+    assert (err.max() / ref.abs().mean()).item() <= MAXABS_REL_TOL
+    for o in outs[1:]:
+        if exact:
+            assert torch.equal(o, outs[0])
+        else:
+            assert ((o.float() - outs[0].float()).abs() <= 2e-3 * outs[0].float().abs() + 1e-6).all()
+    assert not ws[:CUT_RECORD_BYTES].any().item()
+
+
 def _exact_w6ax_chunked(capi, xq, sx, w6, wsc, N, n_chunk=2048):
     """_exact_w6ax for BASELINE-size problems: float64 group sums one slab of output columns at a time."""
     M, K = xq.shape
