@@ -508,6 +508,18 @@ def main():
                 tp_check.append({"layer": name, "mode": mode, "max_abs_over_mean_abs": float(err.max() / ref.abs().mean()),
                                  "rms_rel": float(err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())})
 
+    # ---- BASELINE configs[4] as written: the same tensor-parallel stack with A8 activations (same int8 containers, same
+    # MMAs, only the quantiser's range differs), timed like the main step; every rank takes part
+    c5 = None
+    if world > 1 and xb != 8:
+        for lin in layers:
+            lin.x_bits = 8
+        ms_a8 = timed(step_device, args.steps, 3)
+        for lin in layers:
+            lin.x_bits = xb
+        c5 = {"workload": workload(8), "parallelism": f"tp{world}", "value": total_ops / (ms_a8 * 1e-3) / 1e12, "unit": "TOPS",
+              "ms_per_step": ms_a8, "steps": args.steps}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -518,7 +530,7 @@ def main():
         tops, _, cores, sample = cpu_reference_run(steps=2, warmup=1, sample_rows=32, ab=xb)
         cpu = {"value": tops, "unit": "TOPS", "cores": cores, "kind": "port", "sample": sample}
 
-    extra = None
+    extra = {"c5_w6a8": c5} if c5 else None
     if world == 1 and not args.no_extra:
         extra = extra_records(capi, layers, fp16_w, dev, xb, hbm_gbs)
         del layers, fp16_w, x_dev, outs, pre, pipe

@@ -109,7 +109,7 @@ static int ar_unroll() {
 // 0: free-running grid (up to 4 x 148 blocks of 256 threads).  n > 0: at most n blocks of 1024 threads -- used while a
 // persistent GEMM (one CTA per SM, all of its shared memory) runs on the other SMs: every SM that hosts even one small
 // block of ours is lost to the GEMM, so the reduction is packed onto as few SMs as the GEMM leaves free.
-static int g_ar_blocks = 0;
+static thread_local int g_ar_blocks = 0;      // per host thread (set around the launches of one layer by the thread issuing them)
 void set_allreduce_blocks(int n) { g_ar_blocks = n > 0 ? n : 0; }
 
 // vec0 .. vec1: this rank's range of 16-byte vectors
@@ -274,7 +274,9 @@ int allreduce_sum_f16(void* multicast_ptr, void* const* peer_ptrs, void* const* 
     if (vec1 <= vec0 && !flag_ptrs) return 0;              // synced calls always launch: the peers wait for this rank
     const long long work = vec1 > vec0 ? vec1 - vec0 : 0;
     const int threads = g_ar_blocks > 0 ? 1024 : 256;
-    const long long cap = g_ar_blocks > 0 ? g_ar_blocks : 4 * 148;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const long long cap = g_ar_blocks > 0 ? g_ar_blocks : 4 * sms;
     const int unroll = multicast_ptr ? ar_unroll() : 4;
     long long nb = (work + threads * unroll - 1) / (threads * unroll);
     const int blocks = (int)(nb > cap ? cap : (nb < 1 ? 1 : nb));

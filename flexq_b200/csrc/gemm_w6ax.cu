@@ -1127,7 +1127,7 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 
 // Optional cap on the number of CTAs (= SMs) the persistent GEMM occupies, so that a concurrent kernel on
 // another stream (the peer-memory all-reduce of the previous token chunk) finds free SMs.  0 = all SMs.
-static int g_sm_limit = 0;
+static thread_local int g_sm_limit = 0;       // per host thread: a launch-time setting of the thread that issues the GEMMs
 void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
 
 // per-device caches (a process may drive several GPUs, from several threads): SM count and, per kernel instantiation,

@@ -207,7 +207,7 @@ class TPLinearW6Ax:
         self._comm.wait_stream(cur)                         # the buffer may still be read by earlier work
         lib = capi.load()
         if self._sm_reserve and nch > 1:
-            lib.flexq_set_sm_limit(148 - self._sm_reserve)
+            lib.flexq_set_sm_limit(torch.cuda.get_device_properties(self.w6.device).multi_processor_count - self._sm_reserve)
             lib.flexq_set_allreduce_blocks(self._sm_reserve)
         row = 0
         for c in range(nch):
