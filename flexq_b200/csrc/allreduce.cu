@@ -37,10 +37,20 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Bounded by wall clock, not by polls: a peer stalled on its host (GC, logging, checkpoint I/O) for seconds is ordinary
+// rank skew and must not kill the context; only a rank that stays away for kArTimeoutNs (2 minutes) is taken as missing
+// and the kernel fails instead of hanging the GPU.
+constexpr unsigned long long kArTimeoutNs = 120ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void spin_until(const uint32_t* f, uint32_t epoch) {
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-        if (++spins > (1u << 24)) __trap();                                  // a rank is missing: fail instead of hanging
+        if ((++spins & 0xFFFFu) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > kArTimeoutNs) __trap();
+        }
     }
 }
 // Opening: tell every peer that this rank's data is in place, wait until every peer said the same.  Returns the epoch.
@@ -64,6 +74,7 @@ __device__ __forceinline__ void ar_close(const FlagPtrs& flags, int rank, int wo
     if (threadIdx.x == 0) s_last = (atomicAdd(mine + kFlagTicket, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
     if (s_last) {
+        __threadfence_system();        // acquire side of the ticket: the other CTAs' stores are ordered before the done flags below
         if ((int)threadIdx.x < world) {
             st_release_sys(flags.p[threadIdx.x] + kFlagDone + rank, epoch);
             spin_until(mine + kFlagDone + threadIdx.x, epoch);
