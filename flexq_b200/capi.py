@@ -44,6 +44,7 @@ _SIGNATURES = {
     "flexq_xscale_ref_to_sx": (_i, [_vp, _vp, _i, _i, _vp]),
     "flexq_w6_to_i8": (_i, [_vp, _vp, _i, _i, _vp]),
     "flexq_gemm_w6ax": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "flexq_gemm_w6ax_silu_mul": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "flexq_gemm_w6ax_groupsums": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "flexq_debug_schedule": (_i, [_i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_int), _i, ctypes.POINTER(ctypes.c_int)]),
     "flexq_debug_gemm_trace": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
@@ -277,6 +278,18 @@ def gemm_w6ax(xq, sx, w6, w_scale, N: int, workspace: torch.Tensor, out: torch.T
         out = torch.empty(M, N, dtype=torch.float16, device=xq.device)
     check(load().flexq_gemm_w6ax(_ptr(xq), _ptr(sx), _ptr(w6), _ptr(w_scale), _ptr(out), M, N, K,
                                  _ptr(workspace), workspace.numel(), _stream()), "flexq_gemm_w6ax")
+    return out
+
+
+@_on_device
+def gemm_w6ax_silu_mul(xq, sx, w6_gate_up, w_scale_gate_up, inter: int, workspace: torch.Tensor, out: torch.Tensor | None = None):
+    """gate_up GEMM with SiLU(gate) * up in the epilogue: [M, inter] fp16 from weights packed in the interleaved row
+    order of ``model_pack.interleave_gate_up`` (include/flexq_b200.h: flexq_gemm_w6ax_silu_mul)."""
+    M, K = xq.shape
+    if out is None:
+        out = torch.empty(M, inter, dtype=torch.float16, device=xq.device)
+    check(load().flexq_gemm_w6ax_silu_mul(_ptr(xq), _ptr(sx), _ptr(w6_gate_up), _ptr(w_scale_gate_up), _ptr(out), M, inter, K,
+                                          _ptr(workspace), workspace.numel(), _stream()), "flexq_gemm_w6ax_silu_mul")
     return out
 
 

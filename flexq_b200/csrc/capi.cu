@@ -14,6 +14,7 @@ int pack_planes_i32(const int32_t*, uint32_t*, int, int, int, cudaStream_t);
 int planes_to_i8(const uint32_t*, int8_t*, int, int, int, cudaStream_t);
 int xscale_ref_to_sx(const __half*, float*, int, int, cudaStream_t);
 int gemm_w6ax(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, size_t, cudaStream_t);
+int gemm_w6ax_silu_mul(const int8_t*, const float*, const uint8_t*, const __half*, __half*, int, int, int, void*, size_t, cudaStream_t);
 int gemm_w6ax_groupsums(const int8_t*, const uint8_t*, int32_t*, int, int, int, cudaStream_t);
 int rmsnorm_quant(const __half*, __half*, const __half*, float, __half*, int8_t*, float*, int, int, int, cudaStream_t);
 int silu_mul_quant(const __half*, const __half*, long long, __half*, int8_t*, float*, int, int, int, cudaStream_t);
@@ -105,6 +106,11 @@ int flexq_w6_to_i8(const uint8_t* w6, int8_t* out, int N, int K, void* stream) {
 int flexq_gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale, void* d, int M, int N, int K,
                     void* ws, size_t ws_bytes, void* stream) {
     return gemm_w6ax(xq, sx, w6, (const __half*)w_scale, (__half*)d, M, N, K, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int flexq_gemm_w6ax_silu_mul(const int8_t* xq, const float* sx, const uint8_t* w6_gate_up, const void* w_scale_gate_up, void* h, int M,
+                             int inter, int K, void* ws, size_t ws_bytes, void* stream) {
+    return gemm_w6ax_silu_mul(xq, sx, w6_gate_up, (const __half*)w_scale_gate_up, (__half*)h, M, inter, K, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int flexq_debug_gemm_trace(const int8_t* xq, const float* sx, const uint8_t* w6, const void* w_scale, void* d, int M, int N, int K,

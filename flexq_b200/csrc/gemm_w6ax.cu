@@ -46,6 +46,9 @@ struct GemmParams {
     int P, Pn, R;            // P CTAs: R rows x Pn columns of regular CTAs + (P - R*Pn) spare ones (see Sched)
     int Ureg;                // units [0, Ureg) of every token tile belong to the regular CTAs
     int whole_rows;          // 1: more token tiles than CTAs, every CTA owns whole token tiles
+    int ldd;                 // row pitch of D in elements (N; the number of gate/up pairs with silu)
+    int silu;                // 1: W6 rows alternate 8 gate rows / 8 up rows (flexq_gemm_w6ax_silu_mul); the epilogue writes
+                             // half(silu(half(gate)) * half(up)) for every pair: D is [M][N / 2]
     int cluster;             // > 1: launched as thread-block clusters of this many CTAs, the runs of one weight tile; its
                              // partial sums meet in the first CTA's shared memory (decode tiles, aligned plan)
     long long* trace;        // TRACE builds: [step][16] clock64 stamps of CTA 0
@@ -694,7 +697,68 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const uint32_t stage0 = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u + (uint32_t)(quad >> 1) * 8192u +
                                 (uint32_t)(fc0 + (odd_row ? 1 : 0)) * 128u + 2u * (uint32_t)((lane >> 2) & ~1);
         const uint32_t stage_x = (uint32_t)(4 * (quad & 1)) ^ (uint32_t)(fc0 + (odd_row ? 1 : 0));   // 16-byte column before the k term
+        // SiLU(gate) * up on the fp16-rounded GEMM outputs, arithmetic of silu_mul_quant_kernel (act_quant.cu; reference
+        // activation_kernels.cu:129-144): fp32, __expf, fast division; the caller rounds the product to fp16
+        auto silu_mul = [&](const float g_acc, const float u_acc) {
+            const float g = __half2float(__float2half_rn(kOutScale * g_acc)), u = __half2float(__float2half_rn(kOutScale * u_acc));
+            return __fdividef(g, 1.0f + __expf(-g)) * u;
+        };
         auto store_tile = [&](const int mt, const int nt, const int n, const bool n_ok, const int mbase) {
+            if (p.silu) {
+                // weight rows come in blocks of 8 gate rows followed by their 8 up rows, so a thread of the fragment layout
+                // holds gate (k = 0, 2) and up (k = 1, 3) of the same output columns, a thread of the row layout finds its
+                // partner 8 lanes away; the tile yields 64 output columns: nt * 64 + 16 * (row / 32) + 8 * kk + row % 8
+                if constexpr (C::TSTORE && !DUMP) {
+                    if ((e & 127) == 0) bulk_wait_read_all();
+                    named_bar_sync(2 + wg_id, 128);
+                    const uint32_t sw_ = (uint32_t)(fc0 + (odd_row ? 1 : 0));
+                    const uint32_t base_h = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u + sw_ * 128u + 2u * (uint32_t)((lane >> 2) & ~1);
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++) {
+                        const uint32_t ak = base_h + ((((uint32_t)(2 * quad + kk)) ^ sw_) & 7u) * 16u;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float2 g2 = acc[(2 * kk) * 8 + i], u2 = acc[(2 * kk + 1) * 8 + i];
+                            const float hx = silu_mul(g2.x, u2.x), hy = silu_mul(g2.y, u2.y);
+                            const float keep = odd_row ? hy : hx, send = odd_row ? hx : hy;
+                            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                            const __half2 h = __floats2half2_rn(odd_row ? recv : keep, odd_row ? keep : recv);
+                            sts_u32(ak + (uint32_t)i * 1024u, *reinterpret_cast<const uint32_t*>(&h));
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(2 + wg_id, 128);
+                    if ((e & 127) == 0) {
+                        tma_store_2d(&tmap_d, smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u, nt * 64, mt * M_TILE + col0);
+                        bulk_commit_group();
+                    }
+                } else if constexpr (C::FRAG) {
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++) {
+                        const int hn = nt * 64 + 16 * quad + 8 * kk + (lane >> 2);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int m = mbase + 8 * j + fc0;
+                            const float2 g2 = acc[(2 * kk) * 8 + j], u2 = acc[(2 * kk + 1) * 8 + j];
+                            unsigned short* dst = reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.ldd + hn;
+                            if (hn < p.ldd && m < p.M) __stcs(dst, __half_as_ushort(__float2half_rn(silu_mul(g2.x, u2.x))));
+                            if (hn < p.ldd && m + 1 < p.M) __stcs(dst + p.ldd, __half_as_ushort(__float2half_rn(silu_mul(g2.y, u2.y))));
+                        }
+                    }
+                } else {
+                    const bool gate_lane = ((lane >> 3) & 1) == 0;
+                    const int hn = nt * 64 + 16 * quad + 8 * (lane >> 4) + (lane & 7);
+#pragma unroll
+                    for (int j = 0; j < CPT; j++) {
+                        const int m = mbase + j;
+                        const float a = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
+                        const float other = __shfl_xor_sync(0xffffffffu, a, 8);
+                        if (gate_lane && hn < p.ldd && m < p.M)
+                            __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.ldd + hn, __half_as_ushort(__float2half_rn(silu_mul(a, other))));
+                    }
+                }
+                return;
+            }
             if constexpr (C::TSTORE && !DUMP) {
                 if ((e & 127) == 0) bulk_wait_read_all();            // the previous tile's stores have read the staging tile
                 named_bar_sync(2 + wg_id, 128);
@@ -726,9 +790,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int m = mbase + 8 * j + fc0;
-                        unsigned short* dst = reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n2;
+                        unsigned short* dst = reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.ldd + n2;
                         if (n2 < p.N && m < p.M) __stcs(dst, __half_as_ushort(__float2half_rn(kOutScale * acc[k * 8 + j].x)));
-                        if (n2 < p.N && m + 1 < p.M) __stcs(dst + p.N, __half_as_ushort(__float2half_rn(kOutScale * acc[k * 8 + j].y)));
+                        if (n2 < p.N && m + 1 < p.M) __stcs(dst + p.ldd, __half_as_ushort(__float2half_rn(kOutScale * acc[k * 8 + j].y)));
                     }
                 }
             } else {
@@ -737,7 +801,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     for (int j = 0; j < CPT; j++) {
                         const int m = mbase + j;
                         const float a = kOutScale * ((j & 1) ? acc[j / 2].y : acc[j / 2].x);
-                        if (m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.N + n, __half_as_ushort(__float2half_rn(a)));   // streaming: do not displace X/W in L2
+                        if (m < p.M) __stcs(reinterpret_cast<unsigned short*>(p.D) + (size_t)m * p.ldd + n, __half_as_ushort(__float2half_rn(a)));   // streaming: do not displace X/W in L2
                     }
                 }
             }
@@ -1231,8 +1295,8 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
 
     CUtensorMap tmap_d = tmap_x;
     if (C::TSTORE && !DUMP) {   // D [M][N] fp16 seen as boxes of 64 weight rows (128 bytes, swizzle-128B) x 64 tokens
-        const cuuint64_t dims_d[2] = {(cuuint64_t)p.N, (cuuint64_t)p.M};
-        const cuuint64_t str_d[1] = {(cuuint64_t)p.N * 2};
+        const cuuint64_t dims_d[2] = {(cuuint64_t)p.ldd, (cuuint64_t)p.M};
+        const cuuint64_t str_d[1] = {(cuuint64_t)p.ldd * 2};
         const cuuint32_t box_d[2] = {64u, 64u};
         if (enc(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.D, dims_d, str_d, box_d, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -1339,6 +1403,7 @@ static GemmArgs make_args(const int8_t* xq, const float* sx, const uint8_t* w6, 
         a.p.slots = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCntBytes);
     }
     a.p.M = M; a.p.N = N; a.p.K = K; a.p.G = K / kGroup;
+    a.p.ldd = N; a.p.silu = 0;
     return a;
 }
 
@@ -1348,6 +1413,19 @@ int gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const __half
     if (int e = check_shape(M, N, K)) return e;
     if (workspace_bytes < flexq_gemm_workspace_bytes() || ((uintptr_t)workspace & 15)) return FLEXQ_ERR_WORKSPACE;
     return dispatch<false>(make_args(xq, sx, w6, w_scale, D, nullptr, M, N, K, workspace), stream);
+}
+
+// gate_up GEMM with SiLU(gate) * up applied by the epilogue (first half): w6 / w_scale hold 2 * inter rows,
+// 8 gate rows followed by their 8 up rows (model_pack.interleave_gate_up); H is [M][inter] fp16
+int gemm_w6ax_silu_mul(const int8_t* xq, const float* sx, const uint8_t* w6, const __half* w_scale, __half* H, int M, int inter, int K,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (!xq || !sx || !w6 || !w_scale || !H || !workspace) return FLEXQ_ERR_NULL;
+    if (inter <= 0 || inter % 8) return FLEXQ_ERR_BAD_SHAPE;
+    if (int e = check_shape(M, 2 * inter, K)) return e;
+    if (workspace_bytes < flexq_gemm_workspace_bytes() || ((uintptr_t)workspace & 15)) return FLEXQ_ERR_WORKSPACE;
+    GemmArgs a = make_args(xq, sx, w6, w_scale, H, nullptr, M, 2 * inter, K, workspace);
+    a.p.ldd = inter; a.p.silu = 1;
+    return dispatch<false>(a, stream);
 }
 
 // debug: same GEMM with clock64 stamps of CTA 0's pipeline events (tools/trace.py)

@@ -34,6 +34,9 @@ class QuantLlamaMLP(nn.Module):
         self.hidden_size, self.intermediate_size, self.hidden_act = hidden_size, intermediate_size, hidden_act
         self._fused = None          # (w6 [gate;up], w_scale, versions)
         self._ws = None
+        # True: SiLU(gate) * up is applied by the gate_up GEMM's epilogue (flexq_gemm_w6ax_silu_mul, weights packed in the
+        # interleaved row order) and only [M, inter] fp16 reaches HBM; False: plain gate_up GEMM, then one SiLU*up+quantise pass
+        self.fuse_silu_epilogue = True
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         for m in (self.gate_proj, self.up_proj, self.down_proj):
@@ -48,10 +51,14 @@ class QuantLlamaMLP(nn.Module):
     @torch.no_grad()
     def _pack(self):
         g, u = self.gate_proj, self.up_proj
-        ver = (g.weight.data_ptr(), g.weight._version, u.weight.data_ptr(), u.weight._version)
+        ver = (g.weight.data_ptr(), g.weight._version, u.weight.data_ptr(), u.weight._version, self.fuse_silu_epilogue)
         if self._fused is None or self._fused[2] != ver:
             # per-row-group quantisation: packing the row-concatenated weight == concatenating the packed halves
-            w = torch.cat([g.weight, u.weight], 0).contiguous()
+            if self.fuse_silu_epilogue:
+                from .model_pack import interleave_gate_up
+                w = interleave_gate_up(g.weight, u.weight).contiguous()
+            else:
+                w = torch.cat([g.weight, u.weight], 0).contiguous()
             w = w if w.dtype in (torch.float16, torch.float32) else w.float()
             w6, ws = capi.quant_pack_w6(w)
             self._fused = (w6, ws, ver)
@@ -72,8 +79,12 @@ class QuantLlamaMLP(nn.Module):
         w6_d, ws_d = self.down_proj.pack_weights()
         self._ws = capi.stream_workspace(device=x2.device)
         xq, sx = capi.quant_act(x2, self.gate_proj.act_quantizer.n_bits, self.gate_proj.act_round)
-        gu = capi.gemm_w6ax(xq, sx, w6_gu, ws_gu, 2 * inter, self._ws)
-        hq, sh, h = capi.silu_mul_quant(gu[:, :inter], gu[:, inter:], self.down_proj.act_quantizer.n_bits, want_out=True)
+        if self.fuse_silu_epilogue:
+            h = capi.gemm_w6ax_silu_mul(xq, sx, w6_gu, ws_gu, inter, self._ws)
+            hq, sh = capi.quant_act(h, self.down_proj.act_quantizer.n_bits, capi.ROUND_CUDA)
+        else:
+            gu = capi.gemm_w6ax(xq, sx, w6_gu, ws_gu, 2 * inter, self._ws)
+            hq, sh, h = capi.silu_mul_quant(gu[:, :inter], gu[:, inter:], self.down_proj.act_quantizer.n_bits, want_out=True)
         y = capi.gemm_w6ax(hq, sh, w6_d, ws_d, hid, self._ws)
         if self.down_proj.bias is not None:
             y = y + self.down_proj.bias.to(y.dtype)

@@ -126,6 +126,24 @@ def shard_packed(entry: dict, mode: str, rank: int, world: int) -> dict:
     raise ValueError(f"unknown tensor-parallel mode {mode!r}")
 
 
+def interleave_gate_up(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
+    """[2 * inter, K] weight for ``flexq_gemm_w6ax_silu_mul``: 8 rows of gate_proj, the same 8 rows of up_proj, the next 8 of
+    gate_proj, ... so that one 128-row weight tile of the GEMM holds gate and up of 64 output columns and its epilogue can
+    apply SiLU(gate) * up.  Per-(row, group) quantisation is row-wise, so the packed integers and scales are those of the
+    two layers packed separately."""
+    inter, K = gate_w.shape
+    if up_w.shape != gate_w.shape or inter % 8:
+        raise ValueError("gate_proj / up_proj must have the same [inter, K] shape with inter % 8 == 0")
+    return torch.stack((gate_w.reshape(inter // 8, 8, K), up_w.reshape(inter // 8, 8, K)), dim=1).reshape(2 * inter, K)
+
+
+def deinterleave_gate_up(y: torch.Tensor):
+    """(gate, up) halves of a [..., 2 * inter] tensor laid out by ``interleave_gate_up`` (output of the plain GEMM)."""
+    lead, n2 = y.shape[:-1], y.shape[-1]
+    v = y.reshape(*lead, n2 // 16, 2, 8)
+    return v[..., 0, :].reshape(*lead, n2 // 2), v[..., 1, :].reshape(*lead, n2 // 2)
+
+
 class PackedLinear(nn.Module):
     """Inference-only linear over a packed entry: fused activation quantise + W6Ax GEMM (+ bias)."""
 

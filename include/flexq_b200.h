@@ -114,6 +114,17 @@ int flexq_gemm_w6ax(const int8_t* xq, const float* sx, const uint8_t* w6, const 
                     void* d_half, int M, int N, int K, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* SURVEY 8(f3), first half -- the gate_up GEMM of the MLP with SiLU(gate) * up applied by the GEMM's epilogue, so the
+ * [M][2*inter] fp16 intermediate makes no HBM round trip:
+ *   H[m][j] = half( silu(half(gate[m][j])) * half(up[m][j]) ),  gate / up = the W6Ax GEMM outputs of rows j of gate_proj / up_proj
+ * (fp32 SiLU with __expf and fast division on the fp16-rounded GEMM outputs: the arithmetic of flexq_silu_mul_quant_f16).
+ * w6_gate_up / w_scale_gate_up: the 2*inter rows packed as usual, ordered 8 gate rows, their 8 up rows, 8 gate rows, ...
+ * (flexq_b200.model_pack.interleave_gate_up); inter % 8 == 0.  H is [M][inter] fp16; quantise it with flexq_quant_act.
+ * replaces: the gate / up GEMMs + the activation kernel of  e2e/src/fastertransformer/layers/FfnLayer.cc:371-401,
+ *           kernels/activation_kernels.cu:245-440 (their A8 quantisation stays a separate pass here).             */
+int flexq_gemm_w6ax_silu_mul(const int8_t* xq, const float* sx, const uint8_t* w6_gate_up, const void* w_scale_gate_up_half,
+                             void* h_half, int M, int inter, int K, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug/parity entry: the INT32 per-K-group partial sums S[M][N][K/128] of the same kernel. */
 int flexq_gemm_w6ax_groupsums(const int8_t* xq, const uint8_t* w6, int32_t* S, int M, int N, int K,
                               void* stream);

@@ -662,6 +662,39 @@ def test_gemm_fp16_output_at_baseline_shapes(capi, M, N, K, xb):
         assert torch.equal(S.long().sum(dim=2), (xq.double() @ wq.double().t()).round().long())
 
 
+@pytest.mark.parametrize("M,inter,K", [(1, 1536, 512), (16, 14336, 4096), (48, 1408, 1024), (100, 2048, 1024), (192, 3072, 2048), (300, 11008, 4096),
+                                        (700, 1024, 8192), (2048, 3584, 8192)])
+def test_gemm_silu_mul_epilogue(capi, M, inter, K):
+    """SURVEY 8(f3), first half: flexq_gemm_w6ax_silu_mul (interleaved gate/up rows, SiLU(gate)*up in the GEMM epilogue)
+    against the unfused chain on the same integers -- plain gate_up GEMM, then the SiLU*up pass of flexq_silu_mul_quant_f16.
+    Same fp32 accumulators, same fp16 rounding of gate / up, same SiLU arithmetic: identical fp16 wherever the accumulators
+    are (tiles cut across CTAs may be summed in another order: <= 1 fp16 ulp on gate / up, seen through SiLU*up)."""
+    from flexq_b200 import model_pack
+    dev = torch.device("cuda")
+    torch.manual_seed(M + inter + K)
+    gate_w = (0.03 * torch.randn(inter, K, device=dev)).half()
+    up_w = (0.03 * torch.randn(inter, K, device=dev)).half()
+    x = torch.randn(M, K, device=dev).half()
+    xq, sx = capi.quant_act(x, 6)
+    ws = capi.new_workspace()
+    w6_cat, wsc_cat = capi.quant_pack_w6(torch.cat([gate_w, up_w], 0).contiguous())
+    gu = capi.gemm_w6ax(xq, sx, w6_cat, wsc_cat, 2 * inter, ws)
+    _, _, h_ref = capi.silu_mul_quant(gu[:, :inter], gu[:, inter:], 8, want_out=True)
+    w6_il, wsc_il = capi.quant_pack_w6(model_pack.interleave_gate_up(gate_w, up_w).contiguous())
+    h = capi.gemm_w6ax_silu_mul(xq, sx, w6_il, wsc_il, inter, ws)
+    assert h.shape == (M, inter)
+    # the interleaved weights through the plain GEMM give the same gate / up columns, permuted
+    g2, u2 = model_pack.deinterleave_gate_up(capi.gemm_w6ax(xq, sx, w6_il, wsc_il, 2 * inter, ws))
+    # (tiles cut across CTAs are summed in another order: fp32 rounding, seen relative to the typical magnitude near zeros)
+    tol = 2e-3 * gu.float().abs().mean().item()
+    assert ((g2.float() - gu[:, :inter].float()).abs() <= 2e-3 * gu[:, :inter].float().abs() + tol).all()
+    assert ((u2.float() - gu[:, inter:].float()).abs() <= 2e-3 * gu[:, inter:].float().abs() + tol).all()
+    d = (h.float() - h_ref.float()).abs()
+    assert (d <= 4e-3 * h_ref.float().abs() + 4e-3 * gu[:, inter:].float().abs() + tol).all(), float(d.max())
+    assert (h == h_ref).float().mean().item() >= 0.98
+    assert not ws[:CUT_RECORD_BYTES].any().item()
+
+
 def test_quant_llama_mlp_fused_chain_matches_module_composition(capi):
     """QuantLlamaMLP (one gate_up GEMM + fused SiLU*up+quantise + down GEMM) against the same block composed of three
     QuantLinear modules, which are pinned to the reference's golden outputs elsewhere."""
@@ -684,7 +717,8 @@ def test_quant_llama_mlp_fused_chain_matches_module_composition(capi):
     mlp = QuantLlamaMLP(org, hid, inter, "silu", args)
     mlp.set_quant_state(True, True)
     assert mlp.down_proj.act_quantizer.n_bits == 8 and mlp.gate_proj.act_quantizer.n_bits == 6
-    for shape in ((1, 7, hid), (40, hid)):
+    for shape, fuse in (((1, 7, hid), True), ((40, hid), True), ((300, hid), True), ((40, hid), False), ((300, hid), False)):
+        mlp.fuse_silu_epilogue = fuse          # SiLU*up in the gate_up GEMM's epilogue, or the separate SiLU*up+quantise pass
         x = torch.randn(*shape, device="cuda").half()
         y, h = mlp(x)
         h_ref = torch.nn.functional.silu(mlp.gate_proj(x)) * mlp.up_proj(x)          # module composition (reference forward)

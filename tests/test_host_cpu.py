@@ -275,3 +275,23 @@ def test_gemm_work_decomposition_covers_every_unit_once(m_tiles, n_tiles, G, max
     if m_tiles <= max_ctas:
         # Ureg is rounded to a whole unit: the spare CTAs share that rounding error times the number of token tiles
         assert max(loads) - min(loads) <= max(2, 0.02 * np.mean(loads) + m_tiles / 2), (min(loads), max(loads))
+
+
+def test_interleave_gate_up_layout():
+    """model_pack.interleave_gate_up: 8 gate rows, their 8 up rows, ... (the row order flexq_gemm_w6ax_silu_mul expects),
+    and deinterleave_gate_up is its inverse on the GEMM's output columns."""
+    from flexq_b200 import model_pack
+    inter, K = 40, 6
+    gate = torch.arange(inter * K, dtype=torch.float32).reshape(inter, K)
+    up = -gate - 1
+    w = model_pack.interleave_gate_up(gate, up)
+    assert w.shape == (2 * inter, K)
+    for r in range(2 * inter):
+        blk, j = divmod(r, 16)
+        src = gate if j < 8 else up
+        assert torch.equal(w[r], src[8 * blk + (j % 8)])
+    y = torch.randn(3, 2 * inter)
+    g, u = model_pack.deinterleave_gate_up(y)
+    assert g.shape == (3, inter) and torch.equal(g[:, 8:16], y[:, 16:24]) and torch.equal(u[:, 8:16], y[:, 24:32])
+    with pytest.raises(ValueError):
+        model_pack.interleave_gate_up(gate[:36], up[:36])
