@@ -87,6 +87,9 @@ constexpr uint32_t kBiasB = 32u * 255u * 255u;
 #ifndef FLEXQ_CLUSTER
 #define FLEXQ_CLUSTER 1
 #endif
+#ifndef FLEXQ_EXP_CONSTS
+#define FLEXQ_EXP_CONSTS 0       // measured 2 % slower at M >= 512, 10-40 % on small layers: the expanders wait for the scale block
+#endif
 
 constexpr int kClusterMaxTile = 16;      // largest token tile that sums cut tiles through a thread-block cluster
 
@@ -121,7 +124,13 @@ struct Cfg {
     static constexpr int X_BYTES = GP * M_TILE * 128;              // [GP][M_TILE][128 B], swizzle-128B
     static constexpr int SX_BYTES = GP * M_TILE * 4;               // f32 [GP][M_TILE]
     static constexpr int SW_BYTES = GP * kTileN * 2;               // f16 [GP][128]
-    static constexpr int S_BYTES = SX_BYTES + SW_BYTES;
+    // experiment (off): per-row scale constants (c1, c2) of the bias-MMA epilogue written once per step by the expander
+    // thread that owns the row instead of being recomputed from the fp16 scale by every epilogue warpgroup (LDS.U16 +
+    // convert + 2 FMUL per row and warpgroup -> one LDS.64).  12 fewer instructions per epilogue warp-step, but the
+    // expanders then depend on the scale block: profiles/r2_experiments/sweep_b24_*
+    static constexpr bool XCONST = (FLEXQ_EXP_CONSTS != 0) && (FLEXQ_EPI_FRAG != 0) && (FLEXQ_EPI_WG == 3) && BIAS && GP == 1;
+    static constexpr int CONST_BYTES = XCONST ? kTileN * 8 : 0;
+    static constexpr int S_BYTES = SX_BYTES + SW_BYTES + CONST_BYTES;
     static constexpr int W_BYTES = GP * kTileBytes;                // GP consecutive packed tiles
     static constexpr int NW_FIT = (SMEM_BUDGET - NX * X_BYTES - NS * S_BYTES) / W_BYTES;
     static constexpr int NW = NW_FIT > 10 ? 10 : NW_FIT;
@@ -515,7 +524,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const int s = it % C::NS;
                         const uint32_t dst = smem_base + C::OFF_S + s * C::S_BYTES;
                         producer_wait(bar_s_empty(s), ((it / C::NS) & 1) ^ 1);
-                        mbar_expect_tx(bar_s_full(s), C::S_BYTES);
+                        mbar_expect_tx(bar_s_full(s), C::SX_BYTES + C::SW_BYTES);
                         tma_load_2d(dst, &tmap_sx, mt * M_TILE, g, bar_s_full(s));
                         tma_load_2d(dst + C::SX_BYTES, &tmap_sw, nt * kTileN, g, bar_s_full(s));
                     }
@@ -595,6 +604,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         asm volatile("" : "+r"(w_thread));
         int it = 0, sw = 0;
         uint32_t w_par = 0;
+        int ss_e = 0;
+        uint32_t s_par_e = 0;
         walk_segments(sch, G, [&](const int mt, const int nt, const int g0, const int g1) {
             for (int g = g0; g < g1; g += GP, it++) {
                 const int ng = min(GP, g1 - g);
@@ -620,6 +631,17 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tmem_st32(a_lane + st * C::A_COLS + j * 32, out);   // this row's 128 int8 (value 4*w)
                 }
                 mbar_arrive(bar0 + 8u * (C::NW + sw));   // bar_w_empty(sw): packed tiles consumed
+                if constexpr (C::XCONST && !DUMP) {
+                    // this row's scale constants for the epilogue (see there): after the expansion, so that waiting for the
+                    // scale block (issued with the step's activations) costs nothing the MMA would not wait for anyway; the
+                    // a_full arrive below publishes them (release) along the chain issuer -> commit -> epilogue
+                    mbar_wait(bar_s_full(ss_e), s_par_e);
+                    const uint32_t sblk_e = smem_base + C::OFF_S + (uint32_t)ss_e * C::S_BYTES;
+                    const float swh = __half2float(__ushort_as_half(lds_u16(sblk_e + C::SX_BYTES + (uint32_t)r * 2u)));
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sblk_e + C::SX_BYTES + C::SW_BYTES + (uint32_t)r * 8u),
+                                 "f"(swh * 0x1p100f), "f"(swh * (-(float)kBiasB * 0x1p-49f)) : "memory");
+                    if (++ss_e == C::NS) { ss_e = 0; s_par_e ^= 1u; }
+                }
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_a_full(st));
@@ -675,7 +697,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         // thread part of the scale addresses, kept opaque so that it stays in two registers instead of being rebuilt from
         // the thread index every step; the stage part (sblk) is uniform
         uint32_t sw_off = C::SX_BYTES + (uint32_t)fr0 * 2u, sx_off = (uint32_t)(col0 + fc0) * 4u;
-        asm volatile("" : "+r"(sw_off), "+r"(sx_off));
+        uint32_t sc_off = C::SX_BYTES + C::SW_BYTES + (uint32_t)fr0 * 8u;
+        asm volatile("" : "+r"(sw_off), "+r"(sx_off), "+r"(sc_off));
         const uint32_t bar_s_full0 = s_base + (C::OFF_BAR - C::OFF_S) + 8u * (2 * C::NW);
         const uint32_t bar_s_empty0 = bar_s_full0 + 8u * C::NS;
         const uint32_t bar_acc_empty0 = bar_s_full0 + 8u * (2 * C::NS + C::NAT + C::NX);
@@ -873,8 +896,12 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         // rows beyond N: the scale block is zero-filled by TMA and the row is never stored -- no predicate
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            const float swh = __half2float(__ushort_as_half(lds_u16(sblk + sw_off + 16u * k)));
-                            fc[k] = make_float2(swh * 0x1p100f, swh * (-(float)kBiasB * 0x1p-49f));   // immediates: nothing to keep in registers
+                            if constexpr (C::XCONST) {
+                                fc[k] = lds_f2(sblk + sc_off + 64u * k);     // (sw * 2^100, -B * sw * 2^-49) from the row's expander thread
+                            } else {
+                                const float swh = __half2float(__ushort_as_half(lds_u16(sblk + sw_off + 16u * k)));
+                                fc[k] = make_float2(swh * 0x1p100f, swh * (-(float)kBiasB * 0x1p-49f));   // immediates: nothing to keep in registers
+                            }
                         }
                     }
                     if (!DUMP && !C::FRAG) {
