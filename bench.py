@@ -382,10 +382,11 @@ def main():
     want_peer = os.environ.get("FLEXQ_BENCH_AR", "peer") == "peer"
     ar_chunks = int(os.environ.get("FLEXQ_BENCH_AR_CHUNKS", "2" if world >= 8 else "1"))
     ar_reserve = int(os.environ.get("FLEXQ_BENCH_AR_RESERVE", "8"))
+    ar_mc = os.environ.get("FLEXQ_BENCH_AR_MC", "1" if world >= 8 else "0") == "1"      # NVSwitch multicast (in-switch sum) or peer pointers
     if world > 1 and want_peer:
         try:
             for lin in layers:
-                lin.enable_peer_allreduce(M_TOKENS, chunks=ar_chunks, use_multicast=(world == 8), sm_reserve=ar_reserve)
+                lin.enable_peer_allreduce(M_TOKENS, chunks=ar_chunks, use_multicast=ar_mc, sm_reserve=ar_reserve)
             ar_mode = "peer"
         except Exception as e:                       # noqa: BLE001
             for lin in layers:
