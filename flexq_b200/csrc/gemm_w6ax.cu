@@ -46,6 +46,9 @@ struct GemmParams {
     int P, Pn, R;            // P CTAs: R rows x Pn columns of regular CTAs + (P - R*Pn) spare ones (see Sched)
     int Ureg;                // units [0, Ureg) of every token tile belong to the regular CTAs
     int whole_rows;          // 1: more token tiles than CTAs, every CTA owns whole token tiles
+    int handoff;             // 192-token tile: 1 = cut tiles are summed by parked hand-off (stream-K plan: contributors arrive
+                             // far apart; aligned plan with two runs per tile), 0 = by reductions into a shared slot
+                             // (aligned plan with more runs per tile: they all finish together)
     int ldd;                 // row pitch of D in elements (N; the number of gate/up pairs with silu)
     int silu;                // 1: W6 rows alternate 8 gate rows / 8 up rows (flexq_gemm_w6ax_silu_mul); the epilogue writes
                              // half(silu(half(gate)) * half(up)) for every pair: D is [M][N / 2]
@@ -1034,7 +1037,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     // the CTA's only run (aligned plan): its partial sums stay in registers for the cluster exchange below
                     c_mt = mt; c_nt = nt;
                 } else {
-                    if constexpr (!kHandoff) {
+                    if (!kHandoff || !p.handoff) {
                     // Tile cut by a range boundary, reduction variant: every contributor adds its fp32 partial tile into
                     // the slot of the CTA that owns the tile's first unit with 16-byte vector reductions (thread-linear
                     // layout, a warp covers 512 contiguous bytes) and counts its groups; the one that completes the
@@ -1369,6 +1372,13 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     cfg.attrs = attr;
     // Decode tiles, aligned plan with C runs per weight tile: launch the C CTAs of a tile as one cluster (see kClusterOk in
     // the kernel) when C partial tiles fit the weight ring of the first CTA and the device can hold all clusters at once
+    {   // aligned plan = every CTA walks one run of one tile (plan_ctas): Pn a multiple of n_tiles, no spare CTAs
+        static const int force_handoff = [] { const char* e = getenv("FLEXQ_HANDOFF"); return e ? atoi(e) : -1; }();
+        const bool aligned = !p.whole_rows && p.P == p.R * p.Pn && p.Pn % p.n_tiles == 0;
+        // measured (profiles/r2_experiments/sweep_b27_*): with four or more runs per tile finishing together the completing
+        // CTA of a hand-off waits for too many parked runs (reductions 6-12 % faster); with two, hand-off stays ahead (4-20 %)
+        p.handoff = force_handoff >= 0 ? force_handoff : (aligned && p.Pn / p.n_tiles > 2 ? 0 : 1);
+    }
     p.cluster = 0;
     if (FLEXQ_CLUSTER && !DUMP && M_TILE <= kClusterMaxTile && !p.whole_rows && p.m_tiles == 1 && p.P == p.Pn && p.Pn % p.n_tiles == 0 && cluster_enabled()) {
         const int Cn = p.Pn / p.n_tiles;
