@@ -26,6 +26,7 @@
 // scales), warps 4-7 = weight expanders, warps 8-15 (8-19) = epilogue.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -1228,6 +1229,34 @@ static PFN_tmapEncodeTiled get_encode_fn() {
     return fn;
 }
 
+// Encoded 2-D tensor maps, cached per host thread: the descriptor is a pure function of (pointer, type, shape, pitch, box,
+// swizzle, L2 promotion), so a hit can never be stale, and a decode step that launches the same layers again (eagerly, outside
+// a CUDA graph) skips five driver calls per GEMM.  64 entries, round robin.
+struct TmapKey {
+    const void* ptr; int dtype, swizzle, l2; unsigned long long d0, d1, pitch; unsigned b0, b1;
+};
+static CUresult encode_2d_cached(PFN_tmapEncodeTiled enc, CUtensorMap* out, CUtensorMapDataType dt, void* ptr, const cuuint64_t* dims,
+                                 const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* ones, CUtensorMapSwizzle sw,
+                                 CUtensorMapL2promotion l2) {
+    struct Entry { TmapKey k; CUtensorMap m; bool used; };
+    static thread_local Entry cache[64];
+    static thread_local int next = 0;
+    static const bool enabled = [] { const char* e = getenv("FLEXQ_TMAP_CACHE"); return !(e && e[0] == '0'); }();
+    if (!enabled) return enc(out, dt, 2, ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TmapKey k;
+    memset(&k, 0, sizeof(k));            // padding bytes take part in the comparison
+    k.ptr = ptr; k.dtype = (int)dt; k.swizzle = (int)sw; k.l2 = (int)l2; k.d0 = dims[0]; k.d1 = dims[1]; k.pitch = strides[0]; k.b0 = box[0]; k.b1 = box[1];
+    for (int i = 0; i < 64; i++)
+        if (cache[i].used && memcmp(&cache[i].k, &k, sizeof(k)) == 0) { *out = cache[i].m; return CUDA_SUCCESS; }
+    const CUresult r = enc(out, dt, 2, ptr, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS) {
+        Entry& e = cache[next];
+        next = (next + 1) & 63;
+        e.k = k; e.m = *out; e.used = true;
+    }
+    return r;
+}
+
 // Optional cap on the number of CTAs (= SMs) the persistent GEMM occupies, so that a concurrent kernel on
 // another stream (the peer-memory all-reduce of the previous token chunk) finds free SMs.  0 = all SMs.
 static thread_local int g_sm_limit = 0;       // per host thread: a launch-time setting of the thread that issues the GEMMs
@@ -1297,18 +1326,16 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
         const cuuint64_t dims[2] = {128u, rows};
         const cuuint64_t strides[1] = {128u};
         const cuuint32_t box[2] = {128u, (cuuint32_t)(kTileBytes / 128)};
-        if (enc(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(p.w6), dims, strides, box, ones,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (encode_2d_cached(enc, &tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, const_cast<uint8_t*>(p.w6), dims, strides, box, ones,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS)
             return FLEXQ_ERR_TENSORMAP;
     }
     {   // activations [M][K] int8, box = 128 bytes of k x M_TILE tokens, 128-byte swizzle
         const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
         const cuuint64_t strides[1] = {(cuuint64_t)p.K};
         const cuuint32_t box[2] = {128u, (cuuint32_t)M_TILE};
-        if (enc(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(a.xq), dims, strides, box, ones,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (encode_2d_cached(enc, &tmap_x, CU_TENSOR_MAP_DATA_TYPE_UINT8, const_cast<int8_t*>(a.xq), dims, strides, box, ones,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) != CUDA_SUCCESS)
             return FLEXQ_ERR_TENSORMAP;
     }
     if (!DUMP) {
@@ -1316,16 +1343,14 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
         const cuuint64_t dims_sx[2] = {(cuuint64_t)ldsx, (cuuint64_t)p.G};
         const cuuint64_t str_sx[1] = {(cuuint64_t)ldsx * 4};
         const cuuint32_t box_sx[2] = {(cuuint32_t)M_TILE, (cuuint32_t)GP};
-        if (enc(&tmap_sx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.sx), dims_sx, str_sx, box_sx, ones,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (encode_2d_cached(enc, &tmap_sx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, const_cast<float*>(a.sx), dims_sx, str_sx, box_sx, ones,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE) != CUDA_SUCCESS)
             return FLEXQ_ERR_TENSORMAP;
         const cuuint64_t dims_sw[2] = {(cuuint64_t)p.N, (cuuint64_t)p.G};
         const cuuint64_t str_sw[1] = {(cuuint64_t)p.N * 2};
         const cuuint32_t box_sw[2] = {(cuuint32_t)kTileN, (cuuint32_t)GP};
-        if (enc(&tmap_sw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a.w_scale), dims_sw, str_sw, box_sw, ones,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (encode_2d_cached(enc, &tmap_sw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, const_cast<__half*>(a.w_scale), dims_sw, str_sw, box_sw, ones,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE) != CUDA_SUCCESS)
             return FLEXQ_ERR_TENSORMAP;
     } else {
         tmap_sx = tmap_x;
@@ -1337,8 +1362,8 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
         const cuuint64_t dims_d[2] = {(cuuint64_t)p.ldd, (cuuint64_t)p.M};
         const cuuint64_t str_d[1] = {(cuuint64_t)p.ldd * 2};
         const cuuint32_t box_d[2] = {64u, 64u};
-        if (enc(&tmap_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p.D, dims_d, str_d, box_d, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (encode_2d_cached(enc, &tmap_d, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, p.D, dims_d, str_d, box_d, ones, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE) != CUDA_SUCCESS)
             return FLEXQ_ERR_TENSORMAP;
     }
     p.n_tiles = ceil_div(p.N, kTileN);
