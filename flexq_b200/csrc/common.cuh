@@ -194,10 +194,19 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatil
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
+// the same barrier in two halves: arrive early (does not block), wait where the other CTAs' state is needed
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t addr, uint32_t cta) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
     return r;
+}
+// asynchronous 16-byte store into another CTA's shared memory; the bytes are counted on that CTA's mbarrier (complete_tx)
+__device__ __forceinline__ void st_async_cluster_f4(uint32_t addr, float4 v, uint32_t mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar)
+                 : "memory");
 }
 __device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

@@ -91,10 +91,17 @@ constexpr uint32_t kBiasB = 32u * 255u * 255u;
 #ifndef FLEXQ_CLUSTER
 #define FLEXQ_CLUSTER 1
 #endif
+#ifndef FLEXQ_CLUSTER_ASYNC
+#define FLEXQ_CLUSTER_ASYNC 1     // cluster exchange by st.async + an mbarrier of the first CTA instead of two cluster barriers
+#endif
 #ifndef FLEXQ_EXP_CONSTS
 #define FLEXQ_EXP_CONSTS 0       // measured 2 % slower at M >= 512, 10-40 % on small layers: the expanders wait for the scale block
 #endif
 
+#ifndef FLEXQ_HANDOFF_MIN_TILE
+#define FLEXQ_HANDOFF_MIN_TILE 128
+#endif
+constexpr int kHandoffMinTile = FLEXQ_HANDOFF_MIN_TILE;   // token tiles from this size up sum cut tiles by parked hand-off (run-time rule in launch())
 constexpr int kClusterMaxTile = 16;      // largest token tile that sums cut tiles through a thread-block cluster
 
 template <int M_TILE, int GP>
@@ -149,10 +156,13 @@ struct Cfg {
     static constexpr int OFF_S = OFF_W + NW * W_BYTES;
     static constexpr int OFF_BAR = OFF_S + NS * S_BYTES;
     static constexpr int NDONE = 16;                               // "MMAs of step i retired" ring (> NAB, NAT, NX)
-    static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE;
+    static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE + 1;        // + the cluster exchange's receive barrier
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
     static constexpr int OFF_ONES = (OFF_MISC + 16 + 4 * kMaxParked + 127) / 128 * 128;   // misc: tmem base, flags, parked slot ids
-    static constexpr int SMEM_BYTES = OFF_ONES + ONES_BYTES + 1024; // + alignment slack
+    // cluster exchange (decode tiles, FLEXQ_CLUSTER_ASYNC): room for the partial tiles of up to three other CTAs
+    static constexpr int RECV_BYTES = (FLEXQ_CLUSTER != 0 && FLEXQ_CLUSTER_ASYNC != 0 && M_TILE <= kClusterMaxTile) ? 3 * M_TILE * kTileN * 4 : 0;
+    static constexpr int OFF_RECV = OFF_ONES + ONES_BYTES;
+    static constexpr int SMEM_BYTES = OFF_RECV + RECV_BYTES + 1024; // + alignment slack
     // epilogue warpgroups.  Measured on B200 (70B shapes, M >= 2048): 3 warpgroups of 64 columns (12 warps, 128 regs)
     // beat 2 x 96 columns (8 warps, 200 regs) by 3-8 % on the 192-token tile -- one more warp per scheduler to
     // cover FFMA2 dependencies; 4 x 48 columns are 4 % slower again (per-warp step overhead).  The 128-token
@@ -380,7 +390,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // how tiles cut by a range boundary are summed (see the epilogue): parked partial tiles for the 192-token tile
     // (contributors arrive far apart: measured 2-11 % faster at M >= 512), shared-slot reductions for the smaller
     // tiles, whose contributors finish together (hand-off 5-65 % slower there: the completing CTA waits for the rest)
-    constexpr bool kHandoff = (FLEXQ_FIXUP_HANDOFF != 0) && M_TILE == 192;
+    constexpr bool kHandoff = (FLEXQ_FIXUP_HANDOFF != 0) && M_TILE >= kHandoffMinTile;
     // Decode tiles under the aligned plan run as clusters: the C runs of a weight tile are C consecutive CTAs, which finish
     // together; instead of meeting in global memory (reductions, a fence, an atomic and a load back: 2400-3800 cycles
     // of a 6-12 us kernel) the partial tiles are written into the first CTA's shared memory (the weight ring, idle by
@@ -485,9 +495,20 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             reinterpret_cast<uint4*>(smem + C::OFF_ONES)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         fence_proxy_async_smem();
     }
+    const uint32_t bar_recv = bar0 + 8u * (C::NBAR - 1);
+    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1 && threadIdx.x == 32) {
+        // the first CTA of a cluster will receive (cluster - 1) partial tiles; armed before anyone can send (cluster barrier below)
+        mbar_init(bar_recv, 1);
+        fence_barrier_init();
+        if (blockIdx.x % (uint32_t)p.cluster == 0) mbar_expect_tx(bar_recv, (uint32_t)(p.cluster - 1) * (M_TILE * kTileN * 4));
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // the barrier that orders "receive barrier armed" before "partial tiles sent" is split: every thread arrives here and
+    // waits only where the exchange starts (or at its role's end), microseconds later -- a full cluster barrier in the
+    // prologue cost 1300 cycles of start-up
+    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1) cluster_arrive();
     const uint32_t tmem_base = misc[0];
     if (threadIdx.x == 0) FQ_TRACE(0, 13);
     // Programmatic dependent launch: let the next kernel of the stream start its prologue / weight
@@ -1159,7 +1180,21 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const uint32_t crank = blockIdx.x % (uint32_t)p.cluster;
             constexpr int V4 = CPT / 4;
             constexpr uint32_t kPart = M_TILE * kTileN * 4;          // bytes of one partial tile, thread-linear [quad][thread]
-            const uint32_t mine = smem_base + C::OFF_W + (uint32_t)e * 16u;
+            const uint32_t mine = smem_base + (C::RECV_BYTES > 0 ? C::OFF_RECV : C::OFF_W) + (uint32_t)e * 16u;
+            if constexpr (C::RECV_BYTES > 0) {
+                // the other CTAs send their partial tiles with asynchronous stores that count their bytes on the first CTA's
+                // barrier: no cluster-wide barrier on the tail (two of them cost ~3000 cycles of a 9000-cycle kernel)
+                cluster_wait();
+                if (crank != 0) {
+                    const uint32_t dst = cluster_map_shared(mine + (crank - 1) * kPart, 0), rb = cluster_map_shared(bar_recv, 0);
+#pragma unroll
+                    for (int j = 0; j < V4; j++)
+                        st_async_cluster_f4(dst + (uint32_t)j * C::EPI_THREADS * 16u,
+                                            make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y), rb);
+                } else {
+                    mbar_wait(bar_recv, 0);
+                }
+            } else {
             cluster_sync_all();                                      // every CTA of the cluster has drained its weight ring
             if (crank != 0) {
                 const uint32_t dst = cluster_map_shared(mine + (crank - 1) * kPart, 0);
@@ -1168,6 +1203,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     st_cluster_f4(dst + (uint32_t)j * C::EPI_THREADS * 16u, make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y));
             }
             cluster_sync_all();                                      // the partial tiles have landed in rank 0
+            }
             if (crank == 0) {
                 for (uint32_t rk = 1; rk < (uint32_t)p.cluster; rk++) {      // rank order: the same bits every run
 #pragma unroll
@@ -1183,7 +1219,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     }
 
-    if (kClusterOk && p.cluster > 1 && !(warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG)) {
+    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1 && !(warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG)) cluster_wait();
+    if (kClusterOk && C::RECV_BYTES == 0 && p.cluster > 1 && !(warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG)) {
         cluster_sync_all();      // the two barriers of the epilogue's cluster exchange: every thread of the cluster takes part
         cluster_sync_all();
     }
@@ -1407,7 +1444,7 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
     p.cluster = 0;
     if (FLEXQ_CLUSTER && !DUMP && M_TILE <= kClusterMaxTile && !p.whole_rows && p.m_tiles == 1 && p.P == p.Pn && p.Pn % p.n_tiles == 0 && cluster_enabled()) {
         const int Cn = p.Pn / p.n_tiles;
-        constexpr int kFit = 1 + (C::NW * C::W_BYTES) / (M_TILE * kTileN * 4);
+        constexpr int kFit = C::RECV_BYTES > 0 ? 4 : 1 + (C::NW * C::W_BYTES) / (M_TILE * kTileN * 4);
         if (Cn >= 2 && Cn <= 8 && Cn <= kFit) {
             static std::atomic<int> resident[kMaxDevices][9];         // 1 + clusters of this size the device holds at once (0 = unknown)
             int f = resident[dev][Cn].load(std::memory_order_acquire);
