@@ -196,6 +196,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // the same barrier in two halves: arrive early (does not block), wait where the other CTAs' state is needed
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+// for threads that have published nothing the other CTAs will read (a release arrive is a cluster-scope fence: measured
+// ~1300 cycles when every thread of the CTA executes one)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t addr, uint32_t cta) {
     uint32_t r;

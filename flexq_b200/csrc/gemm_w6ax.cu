@@ -496,18 +496,21 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         fence_proxy_async_smem();
     }
     const uint32_t bar_recv = bar0 + 8u * (C::NBAR - 1);
-    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1 && threadIdx.x == 32) {
-        // the first CTA of a cluster will receive (cluster - 1) partial tiles; armed before anyone can send (cluster barrier below)
-        mbar_init(bar_recv, 1);
-        fence_barrier_init();
-        if (blockIdx.x % (uint32_t)p.cluster == 0) mbar_expect_tx(bar_recv, (uint32_t)(p.cluster - 1) * (M_TILE * kTileN * 4));
+    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1) {
+        // The first CTA of a cluster will receive (cluster - 1) partial tiles: its barrier is armed before anyone can send.
+        // The cluster barrier that orders the two is split -- every thread arrives after the CTA-wide sync below and waits
+        // only where the exchange starts or at its role's end, microseconds later.  (The release arrive is a cluster-scope
+        // fence, ~1300 cycles of start-up; measured alternatives: relaxed arrives for the threads that publish nothing
+        // lose partial tiles, arriving before the sync costs another 800 cycles.)
+        if (threadIdx.x == 32) {
+            mbar_init(bar_recv, 1);
+            fence_barrier_init();
+            if (blockIdx.x % (uint32_t)p.cluster == 0) mbar_expect_tx(bar_recv, (uint32_t)(p.cluster - 1) * (M_TILE * kTileN * 4));
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // the barrier that orders "receive barrier armed" before "partial tiles sent" is split: every thread arrives here and
-    // waits only where the exchange starts (or at its role's end), microseconds later -- a full cluster barrier in the
-    // prologue cost 1300 cycles of start-up
     if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1) cluster_arrive();
     const uint32_t tmem_base = misc[0];
     if (threadIdx.x == 0) FQ_TRACE(0, 13);

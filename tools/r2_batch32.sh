@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out/r2
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2/tests_gpu_b32.txt
+for rep in 1 2; do
+for v in main nocluster; do
+  rt=1; [ $v = nocluster ] && rt=0
+  FLEXQ_CLUSTER_RUNTIME=$rt timeout 900 python tools/sweep.py --models 70b,7b,l3-8b --ms 1,16 --no-cublas --out gpurun_out/r2/sweep_b32_${v}_$rep.jsonl > gpurun_out/r2/sweep_b32_${v}_$rep.log 2>&1
+done
+done
+python tools/trace.py --m 16 --n 4096 --k 4096 --units 12 --cta -1 --noflush > gpurun_out/r2/trace_16_4096_hot_b32.txt 2>&1
+echo done
