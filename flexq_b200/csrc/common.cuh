@@ -200,6 +200,15 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 // ~1300 cycles when every thread of the CTA executes one)
 __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+// a flag word in (another CTA's) shared memory, cluster scope
+__device__ __forceinline__ void st_release_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cluster_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t cluster_map_shared(uint32_t addr, uint32_t cta) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));

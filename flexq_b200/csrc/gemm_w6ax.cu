@@ -53,6 +53,7 @@ struct GemmParams {
     int ldd;                 // row pitch of D in elements (N; the number of gate/up pairs with silu)
     int silu;                // 1: W6 rows alternate 8 gate rows / 8 up rows (flexq_gemm_w6ax_silu_mul); the epilogue writes
                              // half(silu(half(gate)) * half(up)) for every pair: D is [M][N / 2]
+    unsigned nonce;          // cluster exchange: a value no earlier launch left in shared memory (the "armed" flag)
     int cluster;             // > 1: launched as thread-block clusters of this many CTAs, the runs of one weight tile; its
                              // partial sums meet in the first CTA's shared memory (decode tiles, aligned plan)
     long long* trace;        // TRACE builds: [step][16] clock64 stamps of CTA 0
@@ -93,6 +94,9 @@ constexpr uint32_t kBiasB = 32u * 255u * 255u;
 #endif
 #ifndef FLEXQ_CLUSTER_ASYNC
 #define FLEXQ_CLUSTER_ASYNC 1     // cluster exchange by st.async + an mbarrier of the first CTA instead of two cluster barriers
+#endif
+#ifndef FLEXQ_CLUSTER_FLAG
+#define FLEXQ_CLUSTER_FLAG 1      // "receive barrier armed" is published by a flag word instead of a cluster barrier
 #endif
 #ifndef FLEXQ_EXP_CONSTS
 #define FLEXQ_EXP_CONSTS 0       // measured 2 % slower at M >= 512, 10-40 % on small layers: the expanders wait for the scale block
@@ -158,7 +162,7 @@ struct Cfg {
     static constexpr int NDONE = 16;                               // "MMAs of step i retired" ring (> NAB, NAT, NX)
     static constexpr int NBAR = 2 * (NW + NS) + NAT + NX + NAB + NDONE + 1;        // + the cluster exchange's receive barrier
     static constexpr int OFF_MISC = OFF_BAR + NBAR * 8;
-    static constexpr int OFF_ONES = (OFF_MISC + 16 + 4 * kMaxParked + 127) / 128 * 128;   // misc: tmem base, flags, parked slot ids
+    static constexpr int OFF_ONES = (OFF_MISC + 32 + 4 * kMaxParked + 127) / 128 * 128;   // misc: tmem base, flags, parked slot ids
     // cluster exchange (decode tiles, FLEXQ_CLUSTER_ASYNC): room for the partial tiles of up to three other CTAs
     static constexpr int RECV_BYTES = (FLEXQ_CLUSTER != 0 && FLEXQ_CLUSTER_ASYNC != 0 && M_TILE <= kClusterMaxTile) ? 3 * M_TILE * kTileN * 4 : 0;
     static constexpr int OFF_RECV = OFF_ONES + ONES_BYTES;
@@ -505,13 +509,27 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (threadIdx.x == 32) {
             mbar_init(bar_recv, 1);
             fence_barrier_init();
-            if (blockIdx.x % (uint32_t)p.cluster == 0) mbar_expect_tx(bar_recv, (uint32_t)(p.cluster - 1) * (M_TILE * kTileN * 4));
+            if (blockIdx.x % (uint32_t)p.cluster == 0) {
+                mbar_expect_tx(bar_recv, (uint32_t)(p.cluster - 1) * (M_TILE * kTileN * 4));
+                // FLEXQ_CLUSTER_FLAG: "armed" is published through a flag word (this launch's nonce) that one thread of every
+                // other CTA polls over distributed shared memory while it would be waiting for the first MMA anyway -- no
+                // cluster barrier, whose release arrive by every thread costs ~1300 cycles of start-up
+                if (FLEXQ_CLUSTER_FLAG) st_release_cluster_u32(cluster_map_shared(smem_u32(&misc[4 + kMaxParked]), blockIdx.x % (uint32_t)p.cluster), p.nonce);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1) cluster_arrive();
+    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1) {
+        if (!FLEXQ_CLUSTER_FLAG) cluster_arrive();
+        else if (threadIdx.x == 32 && blockIdx.x % (uint32_t)p.cluster != 0) {
+            const uint32_t flag = cluster_map_shared(smem_u32(&misc[4 + kMaxParked]), 0);
+            uint32_t spins = 0;
+            while (ld_acquire_cluster_u32(flag) != p.nonce)
+                if (++spins > (1u << 22)) __trap();
+        }
+    }
     const uint32_t tmem_base = misc[0];
     if (threadIdx.x == 0) FQ_TRACE(0, 13);
     // Programmatic dependent launch: let the next kernel of the stream start its prologue / weight
@@ -1187,7 +1205,8 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if constexpr (C::RECV_BYTES > 0) {
                 // the other CTAs send their partial tiles with asynchronous stores that count their bytes on the first CTA's
                 // barrier: no cluster-wide barrier on the tail (two of them cost ~3000 cycles of a 9000-cycle kernel)
-                cluster_wait();
+                if (FLEXQ_CLUSTER_FLAG) named_bar_sync(1, C::EPI_THREADS);      // thread 32 has seen the first CTA's "armed" flag
+                else cluster_wait();
                 if (crank != 0) {
                     const uint32_t dst = cluster_map_shared(mine + (crank - 1) * kPart, 0), rb = cluster_map_shared(bar_recv, 0);
 #pragma unroll
@@ -1222,7 +1241,7 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     }
 
-    if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1 && !(warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG)) cluster_wait();
+    if (kClusterOk && C::RECV_BYTES > 0 && !FLEXQ_CLUSTER_FLAG && p.cluster > 1 && !(warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG)) cluster_wait();
     if (kClusterOk && C::RECV_BYTES == 0 && p.cluster > 1 && !(warp >= C::EPI_WARP0 && warp < C::EPI_WARP0 + 4 * C::EPI_WG)) {
         cluster_sync_all();      // the two barriers of the epilogue's cluster exchange: every thread of the cluster takes part
         cluster_sync_all();
@@ -1463,7 +1482,11 @@ static int launch(const GemmArgs& a, cudaStream_t stream) {
                 f = 1 + nclusters;
                 resident[dev][Cn].store(f, std::memory_order_release);
             }
-            if (f - 1 >= p.P / Cn) { p.cluster = Cn; na++; }       // a second wave of clusters would double the kernel
+            if (f - 1 >= p.P / Cn) {
+                static std::atomic<unsigned> nonce{0x9E3779B9u};
+                p.cluster = Cn; na++;
+                p.nonce = nonce.fetch_add(0x9E3779B9u, std::memory_order_relaxed) | 1u;
+            }       // a second wave of clusters would double the kernel
         }
     }
     cfg.numAttrs = na;
