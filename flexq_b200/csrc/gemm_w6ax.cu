@@ -500,27 +500,26 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         fence_proxy_async_smem();
     }
     const uint32_t bar_recv = bar0 + 8u * (C::NBAR - 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1) {
-        // The first CTA of a cluster will receive (cluster - 1) partial tiles: its barrier is armed before anyone can send.
-        // The cluster barrier that orders the two is split -- every thread arrives after the CTA-wide sync below and waits
-        // only where the exchange starts or at its role's end, microseconds later.  (The release arrive is a cluster-scope
-        // fence, ~1300 cycles of start-up; measured alternatives: relaxed arrives for the threads that publish nothing
-        // lose partial tiles, arriving before the sync costs another 800 cycles.)
+        // The first CTA of a cluster will receive (cluster - 1) partial tiles on this barrier; it must be armed before anyone
+        // sends.  One thread of an epilogue warp (idle until the first MMA retires) arms it after the CTA-wide sync and
+        // publishes "armed" through a flag word holding this launch's nonce; the same thread of every other CTA polls that
+        // word over distributed shared memory.  Measured alternatives: a cluster barrier split into release arrives here and
+        // waits at the exchange costs ~1300 cycles of start-up (a release arrive is a cluster-scope fence, executed by every
+        // thread), 800 more when the arrives are issued before the sync; relaxed arrives for the threads that publish
+        // nothing lose partial tiles.
         if (threadIdx.x == 32) {
             mbar_init(bar_recv, 1);
             fence_barrier_init();
             if (blockIdx.x % (uint32_t)p.cluster == 0) {
                 mbar_expect_tx(bar_recv, (uint32_t)(p.cluster - 1) * (M_TILE * kTileN * 4));
-                // FLEXQ_CLUSTER_FLAG: "armed" is published through a flag word (this launch's nonce) that one thread of every
-                // other CTA polls over distributed shared memory while it would be waiting for the first MMA anyway -- no
-                // cluster barrier, whose release arrive by every thread costs ~1300 cycles of start-up
                 if (FLEXQ_CLUSTER_FLAG) st_release_cluster_u32(cluster_map_shared(smem_u32(&misc[4 + kMaxParked]), blockIdx.x % (uint32_t)p.cluster), p.nonce);
             }
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
     if (kClusterOk && C::RECV_BYTES > 0 && p.cluster > 1) {
         if (!FLEXQ_CLUSTER_FLAG) cluster_arrive();
         else if (threadIdx.x == 32 && blockIdx.x % (uint32_t)p.cluster != 0) {
