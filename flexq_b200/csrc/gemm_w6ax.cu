@@ -344,7 +344,8 @@ static int plan_ctas(GemmParams& p, int max_ctas, int gp = 1, int fix_steps = 0)
     if (allow_aligned && p.Pn >= p.n_tiles && p.Pn < Umt) {
         const int aligned = p.Pn / p.n_tiles * p.n_tiles, C = aligned / p.n_tiles;
         const int cost_al = steps_of(ceil_div(p.G, C)) + (C > 1 ? (fix_steps + 1) / 2 : 0);
-        const bool enough_sms = gp == 1 || (long long)aligned * p.R * 100 >= (long long)max_ctas * 70;
+        static const int min_sm_pct = [] { const char* e = getenv("FLEXQ_ALIGN_SM_PCT"); return e ? atoi(e) : 70; }();
+        const bool enough_sms = gp == 1 || (long long)aligned * p.R * 100 >= (long long)max_ctas * min_sm_pct;
         if (cost_al <= cost_sk && enough_sms) {
             p.Pn = aligned; p.P = p.R * p.Pn; p.Ureg = (int)Umt;
             return cost_al;
