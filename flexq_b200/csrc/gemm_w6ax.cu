@@ -339,12 +339,13 @@ static int plan_ctas(GemmParams& p, int max_ctas, int gp = 1, int fix_steps = 0)
     // Fewer n-tiles than columns: a whole number C of columns per n-tile cuts every tile into exactly C runs, so every
     // CTA walks one run of one tile -- one cut-tile sum per CTA (none when C = 1) instead of two (a range that straddles
     // a tile boundary ends one tile and starts another).  Taken when its estimated length, with fewer CTAs at work, is
-    // not longer; memory-bound decode tiles (gp > 1) additionally keep >= 70 % of the SMs streaming.
+    // not longer; memory-bound decode tiles (gp > 1) additionally keep >= 55 % of the SMs streaming (measured: 86 and 96
+    // whole-tile CTAs beat 148 stream-K CTAs by 6 and 11 % on the 7B gate_up / qkv layers at M <= 32).
     static const bool allow_aligned = [] { const char* e = getenv("FLEXQ_ALIGN"); return !(e && e[0] == '0'); }();
     if (allow_aligned && p.Pn >= p.n_tiles && p.Pn < Umt) {
         const int aligned = p.Pn / p.n_tiles * p.n_tiles, C = aligned / p.n_tiles;
         const int cost_al = steps_of(ceil_div(p.G, C)) + (C > 1 ? (fix_steps + 1) / 2 : 0);
-        static const int min_sm_pct = [] { const char* e = getenv("FLEXQ_ALIGN_SM_PCT"); return e ? atoi(e) : 70; }();
+        static const int min_sm_pct = [] { const char* e = getenv("FLEXQ_ALIGN_SM_PCT"); return e ? atoi(e) : 55; }();
         const bool enough_sms = gp == 1 || (long long)aligned * p.R * 100 >= (long long)max_ctas * min_sm_pct;
         if (cost_al <= cost_sk && enough_sms) {
             p.Pn = aligned; p.P = p.R * p.Pn; p.Ureg = (int)Umt;
