@@ -15,15 +15,20 @@
 // turns its 96 packed bytes into 128 int8 in registers and writes them to TMEM with one
 // tcgen05.st, where the MMA reads them as its A operand.
 //
-// Work decomposition ("stream-K"): a unit is (n-tile, m-tile, k-group); the U units are split
-// evenly over P persistent CTAs (one per SM).  A CTA walks its units as segments of consecutive
-// groups of one tile, GP groups per pipeline step.  A segment covering all groups of its tile
-// stores fp16 directly; partial segments are summed in an fp32 slot (red.global.add) and the CTA
-// that completes the tile converts, stores and re-zeroes the slot.
+// Work decomposition: a unit is (token tile, n-tile, k-group); P persistent CTAs (one per SM) each walk a contiguous
+// range of units as segments of consecutive groups of one tile, GP groups per pipeline step.  plan_ctas() prices two
+// plans -- stream-K over all CTAs, or (small problems) an aligned plan that cuts every tile into a whole number of runs
+// -- and the host picks the token tile (128 / 192) the same way.  A segment covering all groups of its tile stores fp16
+// directly (fragment layout -> swizzled staging tile -> TMA store); tiles cut by a range boundary are summed by parked
+// hand-off (128- / 192-token tiles), vector reductions into a shared fp32 slot, or a thread-block-cluster exchange
+// through distributed shared memory (16-token tile, aligned plan) -- see the epilogue.
 //
-// Warp roles (512 threads; 640 for the 192-token tile): warp 0 = TMA producer (weights), warps 1,2 = MMA
-// issuers (alternate steps; warp 1 also owns the TMEM allocation), warp 3 = TMA producer (activations +
-// scales), warps 4-7 = weight expanders, warps 8-15 (8-19) = epilogue.
+// Warp roles (CTRL_HIGH layout; 512 threads, 640 for the 192-token tile): epilogue warpgroups first (2 or 3), then the
+// four weight expanders, then W producer (TMA, weights), two MMA issuers (alternate steps; the first owns the TMEM
+// allocation) and X producer (TMA, activations + scales) on the highest warp ids.
+//
+// Experiment switches (-D...) that stayed in the source are off where they measured slower; profiles/r2_experiments/
+// holds the A/B records and DESIGN.md 3.3 the list.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
