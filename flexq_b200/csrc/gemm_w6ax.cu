@@ -1221,6 +1221,9 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                             make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y), rb);
                 } else {
                     mbar_wait(bar_recv, 0);
+                    // un-publish "armed": a CUDA-graph replay launches this kernel again with the same nonce, and shared memory
+                    // keeps its contents between launches
+                    if (FLEXQ_CLUSTER_FLAG && e == 0) misc[4 + kMaxParked] = 0u;
                 }
             } else {
             cluster_sync_all();                                      // every CTA of the cluster has drained its weight ring
