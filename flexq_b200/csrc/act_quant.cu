@@ -252,18 +252,16 @@ __global__ void __launch_bounds__(MAXT) rmsnorm_quant_kernel(const uint4* __rest
         }
     }
     __shared__ float warp_sum[32];
-    __shared__ float s_rstd;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = ss;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_sum[w];
-        s_rstd = rsqrtf(t / (float)K + eps);
-    }
-    __syncthreads();
-    const float rstd = s_rstd;
+    // every warp adds the (<= 32) warp sums itself: one block-wide sync and five shuffles instead of a serial loop on
+    // thread 0 between two syncs (~1000 cycles of a decode-size launch that is all latency)
+    float t = (int)(threadIdx.x & 31) < (int)(blockDim.x >> 5) ? warp_sum[threadIdx.x & 31] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    const float rstd = rsqrtf(t / (float)K + eps);
 #pragma unroll
     for (int u = 0; u < U; u++) {
         const int v = u * blockDim.x + threadIdx.x;
