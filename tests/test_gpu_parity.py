@@ -617,6 +617,25 @@ def test_gemm_decode_cluster_exchange(capi, M, N, K, xb, exact):
         else:
             assert ((o.float() - outs[0].float()).abs() <= 2e-3 * outs[0].float().abs() + 1e-6).all()
     assert not ws[:CUT_RECORD_BYTES].any().item()
+    # the same launches replayed from a CUDA graph (every replay re-uses the launch parameters, the exchange's nonce included)
+    out_g = torch.empty_like(outs[0])
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        capi.gemm_w6ax(xq, sx, w6, wsc, N, ws, out_g)
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(4):
+                capi.gemm_w6ax(xq, sx, w6, wsc, N, ws, out_g)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(5):
+        out_g.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        if exact:
+            assert torch.equal(out_g, outs[0])
+        else:
+            assert ((out_g.float() - outs[0].float()).abs() <= 2e-3 * outs[0].float().abs() + 1e-6).all()
 
 
 def _exact_w6ax_chunked(capi, xq, sx, w6, wsc, N, n_chunk=2048):
