@@ -295,3 +295,34 @@ def test_interleave_gate_up_layout():
     assert g.shape == (3, inter) and torch.equal(g[:, 8:16], y[:, 16:24]) and torch.equal(u[:, 8:16], y[:, 24:32])
     with pytest.raises(ValueError):
         model_pack.interleave_gate_up(gate[:36], up[:36])
+
+
+@pytest.mark.parametrize("m_tiles,n_tiles,G,expect_ctas,expect_cut", [
+    (3, 32, 32, 96, False),      # 4096x4096, M=512: whole tiles on 96 CTAs beat stream-K on 148 (cut-tile sums cost ~16 steps)
+    (4, 32, 32, 128, False),     # ... M=768 (128-token tile at M=512): 128 whole-tile CTAs
+    (1, 32, 32, 128, True),      # one token tile: every weight tile cut into exactly 4 runs
+    (1, 64, 64, 128, True),      # 8192x8192: 2 runs per tile
+    (11, 224, 64, 148, True),    # the bench shape: stream-K over all SMs
+    (2, 64, 64, 128, False),     # 8192x8192, M=256
+])
+def test_gemm_plan_choices(m_tiles, n_tiles, G, expect_ctas, expect_cut):
+    """plan_ctas (csrc/gemm_w6ax.cu) prices the aligned plan against stream-K: CTA count and whether any tile is cut, for
+    the shapes the choice was measured on."""
+    import ctypes
+    from flexq_b200 import capi
+    lib = capi.load()
+    cap = 4096
+    buf = (ctypes.c_int * (5 * cap))()
+    n_ctas = ctypes.c_int(0)
+    lib.flexq_debug_schedule(m_tiles, n_tiles, G, 148, 0, buf, cap, ctypes.byref(n_ctas))
+    assert n_ctas.value == expect_ctas
+    cut = False
+    runs_per_cta = []
+    for cta in range(n_ctas.value):
+        n = lib.flexq_debug_schedule(m_tiles, n_tiles, G, 148, cta, buf, cap, ctypes.byref(n_ctas))
+        segs = np.ctypeslib.as_array(buf)[:5 * n].reshape(n, 5)
+        cut |= bool((segs[:, 4] >= 0).any())
+        runs_per_cta.append(int((segs[:, 4] >= 0).sum()))
+    assert cut == expect_cut
+    if expect_cut and expect_ctas < 148:
+        assert max(runs_per_cta) == 1          # aligned plan: one cut run per CTA
