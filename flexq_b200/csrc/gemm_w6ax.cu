@@ -851,10 +851,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const uint32_t ak = stage0 + (((stage_x ^ (uint32_t)k) & 7u) << 4);
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        const float2 a = acc[k * 8 + i];
+                        const float2 a = __fmul2_rn(acc[k * 8 + i], make_float2(kOutScale, kOutScale));   // exact: a power of two
                         const float keep = odd_row ? a.y : a.x, send = odd_row ? a.x : a.y;
                         const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-                        const __half2 h = __floats2half2_rn(kOutScale * (odd_row ? recv : keep), kOutScale * (odd_row ? keep : recv));
+                        const __half2 h = __floats2half2_rn(odd_row ? recv : keep, odd_row ? keep : recv);
                         sts_u32(ak + (uint32_t)i * 1024u, *reinterpret_cast<const uint32_t*>(&h));
                     }
                 }
