@@ -54,6 +54,26 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end path are allocated on the NUMA node the GPU's PCIe root hangs off (one process per GPU, eight processes
+    otherwise allocate wherever the launcher happened to run).  Returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:                                # noqa: BLE001 -- best effort: no NVML, containerised CPU sets, ...
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region.  The sampler process is started early (its
     start-up takes longer than a short timed region); only samples stamped between begin() and end() are reported.  If the
@@ -345,6 +365,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and os.environ.get("FLEXQ_BENCH_NUMA", "1") == "1":
+        numa = bind_to_gpu_numa_node(local)      # before any pinned host allocation: first touch places the pages
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -563,7 +586,8 @@ def main():
         "e2e": {"value": total_ops / (ms_e2e * 1e-3) / 1e12, "unit": "TOPS", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "bytes_are": "per rank (every rank copies its own shard / row slice)",
                 "path": "pinned host x -> H2D -> fused quantise + GEMM -> D2H -> pinned host y, every layer every step; "
-                        "three streams so copies in both directions overlap the kernels"},
+                        "three streams so copies in both directions overlap the kernels",
+                "numa_cpus_bound": numa},
         "gpu_launches": 2 * len(LAYERS) * args.steps,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "tp_check": tp_check, "extra": extra,
     }
