@@ -338,7 +338,17 @@ static int plan_ctas(GemmParams& p, int max_ctas, int gp = 1, int fix_steps = 0)
     int P_sk = p.R * p.Pn + spare;
     int Ureg = spare ? (int)((Umt * p.R * p.Pn + P_sk / 2) / P_sk) : (int)Umt;
     // every regular CTA and every spare CTA must own at least one unit
-    if (spare && (Ureg < p.Pn || (long long)p.R * (Umt - Ureg) < spare)) { P_sk = p.R * p.Pn; Ureg = (int)Umt; }
+    if (spare && (Ureg < p.Pn || (long long)p.R * (Umt - Ureg) < spare)) { P_sk = p.R * p.Pn; Ureg = (int)Umt; spare = 0; }
+    // A spare CTA walks the tail units of ceil(R / spare) token tiles, and every one of those runs is cut at its head (it
+    // shares a tile with the last regular CTA of that row): extra parked hand-offs that make the spare CTAs the stragglers
+    // of a short kernel (4096x4096, M=2048: 64 us against a median CTA of 55).  Use them only when the steps they take off
+    // everybody else outweigh that.
+    static const bool spare_model = [] { const char* e = getenv("FLEXQ_SPARE_MODEL"); return !(e && e[0] == '0'); }();
+    if (spare && spare_model) {
+        const long long steps_with = steps_of((Umt * p.R + P_sk - 1) / P_sk), steps_without = steps_of((Umt + p.Pn - 1) / p.Pn);
+        const long long extra_cuts = (p.R + spare - 1) / spare;                  // row-head runs per spare CTA
+        if (steps_with + extra_cuts * ((fix_steps + 2) / 3) >= steps_without) { P_sk = p.R * p.Pn; Ureg = (int)Umt; spare = 0; }
+    }
     const bool sk_cuts = (Umt * p.R) % P_sk != 0 || (Umt * p.R / P_sk) % p.G != 0;
     const int cost_sk = steps_of((Umt * p.R + P_sk - 1) / P_sk) + (sk_cuts ? fix_steps : 0);
     // Fewer n-tiles than columns: a whole number C of columns per n-tile cuts every tile into exactly C runs, so every
