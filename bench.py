@@ -36,9 +36,9 @@ LAYERS = [("attn_o_8192x8192", 8192, 8192, "row"),
           ("mlp_down_8192x28672", 8192, 28672, "row")]
 # dram__bytes_read.sum + dram__bytes_write.sum of one captured launch (28672x8192, M=2048): a CONSTANT taken from the ncu
 # capture committed as profiles/ncu_prefill_r2.txt (ncu is not run inside the bench), stated as such in the JSON line
-NCU_TRAFFIC_BYTES = 217.55e6 + 111.79e6
-NCU_TRAFFIC_NOTE = ("constant from profiles/ncu_prefill_r2.txt (ncu --set full of the 28672x8192 M=2048 launch: 217.5 MB read + "
-                    "111.8 MB written), not measured in this run; algorithmic bytes of that launch 314 MB (packed W 176 + X 17 + D 117 + scales 4)")
+NCU_TRAFFIC_BYTES = 224.54e6 + 114.07e6
+NCU_TRAFFIC_NOTE = ("constant from profiles/ncu_prefill_r2.txt (ncu --set full of the 28672x8192 M=2048 launch: 224.5 MB read + "
+                    "114.1 MB written), not measured in this run; algorithmic bytes of that launch 314 MB (packed W 176 + X 17 + D 117 + scales 4)")
 
 
 def workload(xb):
