@@ -781,16 +781,10 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         constexpr bool PREFETCH = (FLEXQ_EPI_PREFETCH != 0) && GP == 1 && ((CPT / CH) % 2 == 0) && !kRearm;
         bool pre = false;
         const int n_steps = sch.b - sch.a;
-        // Finished tile -> D.  Fragment layout with staging (TSTORE): lanes l and l ^ 4 hold neighbouring weight rows of the
-        // same two tokens; one exchange gives each a (row, row + 1) pair of one token, packed to a half2 and stored to the
-        // warpgroup's staging tile ([token][64 rows] boxes, swizzle-128B: the 8 token rows a warp touches land in 8
-        // different 16-byte columns, conflict free); one thread per warpgroup then issues two TMA stores (rows / tokens
-        // beyond N / M are clipped by the tensor map).  2-byte global stores straight from the fragment cost the LSU a
+        // Finished tile -> D.  Fragment layout with staging (TSTORE): every thread converts its values to fp16 and stores them
+        // to the warpgroup's staging tile ([token][64 rows] boxes, swizzle-128B); one thread per warpgroup then issues two
+        // TMA stores (rows / tokens beyond N / M are clipped by the tensor map).  2-byte global stores straight from the fragment cost the LSU a
         // sector per 16 bytes (measured: 8 % of the epilogue's stall samples at K = 8192, proportionally more at smaller K).
-        const bool odd_row = (lane >> 2) & 1;
-        const uint32_t stage0 = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u + (uint32_t)(quad >> 1) * 8192u +
-                                (uint32_t)(fc0 + (odd_row ? 1 : 0)) * 128u + 2u * (uint32_t)((lane >> 2) & ~1);
-        const uint32_t stage_x = (uint32_t)(4 * (quad & 1)) ^ (uint32_t)(fc0 + (odd_row ? 1 : 0));   // 16-byte column before the k term
         // SiLU(gate) * up on the fp16-rounded GEMM outputs, arithmetic of silu_mul_quant_kernel (act_quant.cu; reference
         // activation_kernels.cu:129-144): fp32, __expf, fast division; the caller rounds the product to fp16
         auto silu_mul = [&](const float g_acc, const float u_acc) {
@@ -805,19 +799,16 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if constexpr (C::TSTORE && !DUMP) {
                     if ((e & 127) == 0) bulk_wait_read_all();
                     named_bar_sync(2 + wg_id, 128);
-                    const uint32_t sw_ = (uint32_t)(fc0 + (odd_row ? 1 : 0));
-                    const uint32_t base_h = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u + sw_ * 128u + 2u * (uint32_t)((lane >> 2) & ~1);
+                    const uint32_t rowbase = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u + (uint32_t)fc0 * 128u + 2u * (uint32_t)(lane >> 2);
 #pragma unroll
                     for (int kk = 0; kk < 2; kk++) {
-                        const uint32_t ak = base_h + ((((uint32_t)(2 * quad + kk)) ^ sw_) & 7u) * 16u;
+                        const uint32_t ch = (uint32_t)(2 * quad + kk);       // 16-byte column of output columns 16 * quad + 8 * kk + 0..7
+                        const uint32_t off0 = ((ch ^ (uint32_t)fc0) & 7u) << 4, off1 = 128u + (((ch ^ (uint32_t)(fc0 + 1)) & 7u) << 4);
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             const float2 g2 = acc[(2 * kk) * 8 + i], u2 = acc[(2 * kk + 1) * 8 + i];
-                            const float hx = silu_mul(g2.x, u2.x), hy = silu_mul(g2.y, u2.y);
-                            const float keep = odd_row ? hy : hx, send = odd_row ? hx : hy;
-                            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-                            const __half2 h = __floats2half2_rn(odd_row ? recv : keep, odd_row ? keep : recv);
-                            sts_u32(ak + (uint32_t)i * 1024u, *reinterpret_cast<const uint32_t*>(&h));
+                            sts_u16(rowbase + (uint32_t)i * 1024u + off0, __half_as_ushort(__float2half_rn(silu_mul(g2.x, u2.x))));
+                            sts_u16(rowbase + (uint32_t)i * 1024u + off1, __half_as_ushort(__float2half_rn(silu_mul(g2.y, u2.y))));
                         }
                     }
                     fence_proxy_async_smem();
@@ -856,16 +847,23 @@ w6ax_gemm_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if constexpr (C::TSTORE && !DUMP) {
                 if ((e & 127) == 0) bulk_wait_read_all();            // the previous tile's stores have read the staging tile
                 named_bar_sync(2 + wg_id, 128);
+                // every thread stores its own halves: 2 conversions + 2 st.shared.u16 per value pair (an exchange with the
+                // neighbouring row's lane for one packed st.shared.u32 -- shuffle + 4 selects -- measured no faster); the 8 lanes
+                // of a row octet fill one 16-byte column, the 4 token rows of a warp land in 4 different columns (swizzle):
+                // conflict free
+                {
+                    const uint32_t rowbase = smem_base + C::OFF_STAGE + (uint32_t)wg_id * 16384u + (uint32_t)(quad >> 1) * 8192u +
+                                             (uint32_t)fc0 * 128u + 2u * (uint32_t)(lane >> 2);
+                    const uint32_t c0 = (uint32_t)(4 * (quad & 1));
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t ak = stage0 + (((stage_x ^ (uint32_t)k) & 7u) << 4);
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t off0 = (((c0 | (uint32_t)k) ^ (uint32_t)fc0) & 7u) << 4, off1 = 128u + ((((c0 | (uint32_t)k) ^ (uint32_t)(fc0 + 1)) & 7u) << 4);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float2 a = __fmul2_rn(acc[k * 8 + i], make_float2(kOutScale, kOutScale));   // exact: a power of two
-                        const float keep = odd_row ? a.y : a.x, send = odd_row ? a.x : a.y;
-                        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-                        const __half2 h = __floats2half2_rn(odd_row ? recv : keep, odd_row ? keep : recv);
-                        sts_u32(ak + (uint32_t)i * 1024u, *reinterpret_cast<const uint32_t*>(&h));
+                        for (int i = 0; i < 8; i++) {
+                            const float2 a = __fmul2_rn(acc[k * 8 + i], make_float2(kOutScale, kOutScale));   // exact: a power of two
+                            sts_u16(rowbase + (uint32_t)i * 1024u + off0, __half_as_ushort(__float2half_rn(a.x)));
+                            sts_u16(rowbase + (uint32_t)i * 1024u + off1, __half_as_ushort(__float2half_rn(a.y)));
+                        }
                     }
                 }
                 fence_proxy_async_smem();
